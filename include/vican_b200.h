@@ -1,0 +1,183 @@
+/* vican_b200 -- C ABI of the B200-native bipartite SE(3) synchronisation solver.
+ *
+ * The reference (gabmoreira/vican) is pure Python and has NO plugin / FFI boundary for this
+ * path: its boundary is the two Python functions
+ *     vican/bipgo.py:353  bipartite_se3sync(...)
+ *     vican/bipgo.py:493  object_bipartite_se3sync(...)
+ * The drop-in keeps those signatures in Python (vican_b200/bipgo.py) and calls the entry
+ * points below through ctypes.  Each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors) unless the name
+ *    starts with h_; the library never allocates device memory (workspace sizes are queried);
+ *  - `stream` is a cudaStream_t passed as void*; work is asynchronous on it unless stated;
+ *  - return value: 0 = OK, < 0 = -(cudaError_t), > 0 = solver status (VB_STATUS_*);
+ *  - 3x3 blocks are row-major, 9 doubles; all arithmetic is fp64.
+ */
+#ifndef VICAN_B200_H
+#define VICAN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_STATUS_OK 0
+#define VB_STATUS_NOT_CONVERGED 1   /* CG hit maxiter (reference: assert exit_code == 0, bipgo.py:478) */
+#define VB_STATUS_EIG_STALLED 2     /* LOBPCG hit max_inner before tol (result still returned) */
+#define VB_STATUS_BAD_ARGUMENT 3
+
+/* Device-resident bipartite graph of aggregated (camera, time) edges, stored twice:
+ * sorted by time node (CSR) and sorted by camera (CSC) with camera tiles for the camera
+ * pass.  Built by vb_ingest_* from the raw detections (replaces the dict / COO / CSR
+ * assembly of bipgo.py:203-276). */
+typedef struct vb_graph {
+    int64_t n_c;            /* cameras (global) */
+    int64_t n_t;            /* time nodes (local to this rank) */
+    int64_t n_edges;        /* aggregated edges E (local) */
+    int64_t n_tiles;        /* camera tiles */
+    const int32_t* t_rowptr;   /* [n_t+1] */
+    const int32_t* t_cam;      /* [E]   camera of each time-sorted edge */
+    const double*  t_B;        /* [E][9] block  sum k_r R_cm R_m^T R_0 */
+    const double*  t_w;        /* [E]   sum k_t^2   (translation Laplacian weight) */
+    const int32_t* c_colptr;   /* [n_c+1] */
+    const int32_t* c_time;     /* [E]   time node of each camera-sorted edge */
+    const double*  c_B;        /* [E][9] */
+    const double*  c_w;        /* [E] */
+    const int32_t* tile_cam;   /* [n_tiles] */
+    const int32_t* tile_start; /* [n_tiles] */
+    const int32_t* tile_end;   /* [n_tiles] */
+    const double*  deg_t;      /* [n_t]  sum of k_r over the node's edges (bipgo.py:271) */
+    const double*  deg_c;      /* [n_c]  sum of k_r over the camera's LOCAL edges (bipgo.py:275) */
+} vb_graph;
+
+/* Optional cross-rank reduction hook (edge-sharded multi-GPU): called on `stream` after every
+ * camera pass with the camera-side accumulator.  NULL on a single GPU. */
+typedef int (*vb_allreduce_fn)(void* ctx, double* buf, int64_t count, void* stream);
+
+typedef struct vb_so3_options {
+    int32_t maxiter;        /* primal-dual iterations (bipgo.py:282) */
+    int32_t max_inner;      /* cap on LOBPCG steps per outer iteration */
+    double  tol;            /* eigen-residual tolerance relative to rms(Lambda_C) */
+    vb_allreduce_fn allreduce;
+    void*   allreduce_ctx;
+} vb_so3_options;
+
+typedef struct vb_so3_stats {
+    int32_t outer_done;
+    int32_t time_passes;    /* launches of the time-sorted edge pass */
+    int32_t cam_passes;     /* launches of the camera-sorted edge pass */
+    int32_t lobpcg_steps;   /* cooperative LOBPCG kernels */
+    int32_t kernel_launches;
+    int32_t stalled_outer;  /* outer iterations whose eigen-solve hit max_inner */
+    double  theta[3];       /* last Ritz values (the reference's evals0..2, bipgo.py:336-339) */
+    double  resid[3];       /* last eigen-residual norms */
+    double  anorm;
+    int32_t inner_per_outer[64];
+} vb_so3_stats;
+
+const char* vb_version(void);
+const char* vb_status_string(int code);
+
+/* ---- batched geometry (vican/geometry.py) ------------------------------------------------ */
+/* SE3.__matmul__ (geometry.py:260-261).  round_f32 != 0 rounds the result to float32 as the
+ * reference's float32 4x4 cache does. */
+int vb_se3_compose_batch(const double* Ra, const double* ta, const double* Rb, const double* tb,
+                         double* Rout, double* tout, int64_t n, int round_f32, void* stream);
+/* SE3.inv (geometry.py:235-243): R^T, -R^T t; round_f32 != 0 mirrors the float32 store. */
+int vb_se3_invert_batch(const double* R, const double* t, double* Rinv, double* tinv, int64_t n,
+                        int round_f32, void* stream);
+/* project_SO3 (geometry.py:175-191): U diag(1,1,det(U V^T)) V^T, one thread per block. */
+int vb_polar_so3_batch(const double* M, double* R, int64_t n, void* stream);
+/* The three SVD factors used by the primal/dual updates (bipgo.py:306-312, :323-329);
+ * any output may be NULL. */
+int vb_svd3_factors_batch(const double* M, double* rot, double* sym_pos, double* sym_inv, int64_t n,
+                          void* stream);
+
+/* ---- ingestion (bipgo.py:203-276, :420-431) ---------------------------------------------- */
+/* Raw detections are given as flat arrays (already filtered by edge_filter on the host):
+ * cam/time/marker indices, detection rotation R[E_raw][9], weights k_r, k_t.  markerC[m] =
+ * R_m^T R_0 (constraint fold, bipgo.py:209-213).  round_kr_f32 mirrors numpy's float32
+ * product k_r * R when the pose arrays are float32 (object variant, geometry.py:209-211).  */
+int64_t vb_ingest_workspace_bytes(int64_t n_raw);
+/* step 1: sort raw detections by (time, camera), count aggregated pairs.  Writes raw_perm
+ * [n_raw] (sorted position -> raw index), raw_pair [n_raw] (pair id per sorted position) and
+ * returns the number of pairs in *h_n_pairs (host; synchronises the stream). */
+int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64_t n_c, int64_t n_t,
+                   int32_t* raw_perm, int32_t* raw_pair, int64_t* h_n_pairs, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* step 2: fold + aggregate into the time-sorted arrays, build the camera-sorted copy, row /
+ * column pointers, degrees and camera tiles.  pair_start [E+1] (into the sorted raw list) and
+ * c_perm [E] (camera-sorted position -> time-sorted edge) are kept for the translation stage.
+ * tile_len = max edges per camera tile; tile arrays must hold vb_ingest_max_tiles entries. */
+int64_t vb_ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len);
+int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* marker, const double* R,
+                    const double* k_r, const double* k_t, const double* markerC, int64_t n_raw,
+                    int round_kr_f32, const int32_t* raw_perm, const int32_t* raw_pair, int64_t n_pairs,
+                    int64_t n_c, int64_t n_t, int64_t tile_len,
+                    int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
+                    int32_t* pair_start, int32_t* c_colptr, int32_t* c_time, double* c_B, double* c_w,
+                    int32_t* c_perm, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_end,
+                    int64_t* h_n_tiles, double* deg_t, double* deg_c, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+/* ---- rotation stage (bipgo.py:243-348) --------------------------------------------------- */
+/* One edge pass each (exposed for tests and for the roofline measurement):
+ *   vb_pass_time: out_t = [Lambda_T[t]] * sum_{e in t} B_e^T X[c_e]   (mode 0 with lamT, mode 1 raw sum)
+ *   vb_pass_cam : Y_c  += sum_{e in c} B_e W[t_e]                      (Y must be zeroed by the caller) */
+int vb_pass_time(const vb_graph* g, int mode, const double* X, const double* lamT, double* out, void* stream);
+int vb_pass_cam(const vb_graph* g, const double* W, double* Y, void* stream);
+/* Per-node updates: primal (bipgo.py:306-315): r_c, Lambda_C = U S U^T, Lambda_C^-1;
+ * dual (bipgo.py:323-332): r_t, Lambda_T = U S^-1 U^T, and Wt = Lambda_T Y_t. */
+int vb_primal_update(const double* M, double* r_c, double* lamC, double* lamCinv, int64_t n_c, void* stream);
+int vb_dual_update(const double* Yt, double* r_t, double* lamT, double* Wt, int64_t n_t, void* stream);
+/* Gauge + projection (bipgo.py:295-297): X_c <- project_SO3(V_c V_0^-1). */
+int vb_gauge_project(const double* V, double* r_c, int64_t n_c, void* stream);
+
+int64_t vb_so3sync_workspace_bytes(int64_t n_c, int64_t n_t);
+/* Whole primal-dual loop.  Outputs r_c [n_c][9], r_t [n_t][9] as stored by the reference
+ * BEFORE its final transpose (bipgo.py:344-348): world rotations are the transposes.
+ * Synchronises the stream (reads convergence flags).  stats may be NULL. */
+int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, double* r_t,
+                   void* workspace, int64_t workspace_bytes, vb_so3_stats* stats, void* stream);
+
+/* ---- translation stage (bipgo.py:420-487) ------------------------------------------------ */
+/* Per aggregated pair g_p = sum_{raw e in p} k_t^2 d_e with
+ *   d_e = Rw_c t_cm + Rw_t q_m,  q_m = (R_0^T R_m) (T_m^-1 T_0).t   (bipgo.py:451-455),
+ * Rw = world rotations (transposes of r_c / r_t).  Also writes d_raw [n_raw][3] in sorted order
+ * when non-NULL (needed by LSQR).  rhs = J^T t~ : rhs_c [n_c][3] (caller zeroes), rhs_t [n_t][3]. */
+int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
+                 const double* t_cm, const double* k_t, const double* marker_q, const double* r_c,
+                 const double* r_t, const int32_t* t_time, const int32_t* c_perm, double* pair_g,
+                 double* d_sorted, double* rhs_c, double* rhs_t, void* stream);
+int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t);
+/* Conjugate gradients on J^T J x = J^T t~ replaying scipy.sparse.linalg.cg as the reference
+ * calls it (bipgo.py:477: x0 = 0, no preconditioner, rtol = 1e-5, atol = 0, maxiter = 10 * 3N,
+ * ||r|| tested before each step).  jacobi != 0 switches to the Jacobi-preconditioned variant
+ * (accurate mode; not the reference iteration).  x_c [n_c][3], x_t [n_t][3]. */
+int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t,
+                double rtol, int64_t maxiter, int jacobi, int32_t* h_iters, void* workspace,
+                int64_t workspace_bytes, vb_allreduce_fn allreduce, void* allreduce_ctx, void* stream);
+int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw);
+/* LSQR on J x = t~ replaying scipy.sparse.linalg.lsqr defaults (bipgo.py:480: damp 0,
+ * atol = btol = 1e-6, conlim 1e8, iter_lim = 2 * 3N).  Rows are the raw detections in sorted
+ * order: k_t (x_t - x_c) = k_t d_e. */
+int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw_pair, const int32_t* pair_start,
+                  const int32_t* t_time, const double* k_t, const double* d_sorted, int64_t n_raw, double* x_c, double* x_t,
+                  double atol, double btol, double conlim, int64_t iter_lim, int32_t* h_istop,
+                  int32_t* h_iters, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- multi-GPU (edge-sharded by time-node range, one process per GPU) ---------------------- */
+/* NCCL is resolved at run time (dlopen); the reference has no distributed code, these exist so
+ * that vb_so3sync_run / vb_trans_cg can sum camera-side accumulators across ranks. */
+int vb_nccl_available(void);
+int vb_nccl_unique_id(void* h_out128, int64_t bytes);                 /* rank 0, then broadcast */
+int vb_nccl_init(const void* h_id128, int64_t bytes, int rank, int nranks, void** ctx_out);
+int vb_nccl_destroy(void* ctx);
+int vb_nccl_allreduce(void* ctx, double* buf, int64_t count, void* stream);   /* a vb_allreduce_fn */
+void* vb_nccl_allreduce_fn(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VICAN_B200_H */

@@ -1,0 +1,280 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path, called through the
+C ABI, against the CPU oracle / the committed reference goldens on identical inputs.
+
+Tolerances are BASELINE.json's: rotation geodesic error <= 1e-6 rad, relative translation
+error <= 1e-6 per node (fp64)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import device_model as dm            # noqa: E402
+from oracle import vican_oracle as orc           # noqa: E402
+from vican_b200 import synthetic as syn          # noqa: E402
+from vican_b200.geometry import SE3, geodesic_rad, rel_translation_err  # noqa: E402
+
+from util import ROT_TOL_RAD, TRANS_REL_TOL, callables, compare, golden_names, load_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from vican_b200 import _cabi
+    return _cabi.lib()
+
+
+def _arrays(g, filt=True):
+    keep = g.reproj < 0.5 if filt else np.ones(g.n_edges, bool)
+    cam, time, marker = g.cam[keep], g.time[keep], g.marker[keep]
+    uc, ci = np.unique(cam, return_inverse=True)
+    ut, ti = np.unique(time, return_inverse=True)
+    return dict(cam=ci.astype(np.int32), time=ti.astype(np.int32), marker=marker.astype(np.int32), R=g.R[keep],
+                t=g.t[keep], k_r=g.w[keep], k_t=2.0 * g.w[keep], n_c=len(uc), n_t=len(ut))
+
+
+def _device_graph(g, a, **kw):
+    from vican_b200.solver import DeviceGraph
+    C_m = np.transpose(g.marker_R, (0, 2, 1)) @ g.marker_R[0]
+    return DeviceGraph(a["cam"], a["time"], a["marker"], a["R"], a["k_r"], a["k_t"], C_m, a["n_c"], a["n_t"], **kw)
+
+
+def _oracle_pairs(g, a):
+    blk = orc.fold_blocks(a["R"], a["k_r"], a["marker"], g.marker_R, 0)
+    return orc.aggregate_pairs(a["cam"].astype(np.int64), a["time"].astype(np.int64), blk, a["k_r"], a["n_t"])
+
+
+# ------------------------------------------------------------------------------- kernels
+def test_svd3_factors_kernel_vs_numpy(cuda):
+    from vican_b200 import ops
+    rng = np.random.default_rng(0)
+    M = rng.standard_normal((4096, 3, 3)) * rng.uniform(0.1, 50.0, (4096, 1, 1))
+    M[:64, :, 0] *= -1
+    rot, sp, si = [x.cpu().numpy() for x in ops.svd3_factors_batch(M)]
+    r0, U, S = orc.svd_polar_batch(M)
+    Ut = np.transpose(U, (0, 2, 1))
+    p0 = (U * S[:, None, :]) @ Ut
+    i0 = (U * (1 / S)[:, None, :]) @ Ut
+    cond = (S[:, 0] / S[:, 2])[:, None, None]
+    assert np.all(np.abs(rot - r0) < 1e-13 * cond)
+    assert np.all(np.abs(sp - p0) < 1e-13 * cond * S[:, :1, None])
+    assert np.all(np.abs(si - i0) < 1e-13 * cond * cond / S[:, 2:, None])
+    pol = ops.polar_so3_batch(M).cpu().numpy()
+    assert np.abs(pol - rot).max() == 0.0
+
+
+def test_se3_batch_kernels_vs_container(cuda):
+    from vican_b200 import ops
+    rng = np.random.default_rng(1)
+    n = 500
+    Ra, Rb = syn.random_rotations(rng, n), syn.random_rotations(rng, n)
+    ta, tb = rng.normal(0, 3, (n, 3)), rng.normal(0, 3, (n, 3))
+    Ri, ti = ops.se3_invert_batch(Ra, ta, round_f32=True)
+    Ri, ti = Ri.cpu().numpy(), ti.cpu().numpy()
+    Rc, tc = ops.se3_compose_batch(Ra, ta, Rb, tb)
+    Rc, tc = Rc.cpu().numpy(), tc.cpu().numpy()
+    for i in range(0, n, 7):
+        a, b = SE3(R=Ra[i], t=ta[i]), SE3(R=Rb[i], t=tb[i])
+        inv = a.inv()                                    # float32 store, as the reference
+        assert np.array_equal(Ri[i].astype(np.float32), inv.R())
+        assert np.abs(ti[i].astype(np.float32) - inv.t()).max() <= 1e-6 * np.abs(inv.t()).max()
+        assert np.abs(Rc[i] - Ra[i] @ Rb[i]).max() < 1e-15 * 4
+        assert np.abs(tc[i] - (Ra[i] @ tb[i] + ta[i])).max() < 1e-14
+    Ri64, ti64 = ops.se3_invert_batch(Ra, ta)
+    assert np.abs(Ri64.cpu().numpy() - np.transpose(Ra, (0, 2, 1))).max() == 0.0
+    assert np.abs(ti64.cpu().numpy() + np.einsum("nji,nj->ni", Ra, ta)).max() < 1e-14
+
+
+@pytest.mark.parametrize("shape", [(12, 80, 4, 4, 2), (20, 300, 6, 7, 3), (40, 500, 24, 20, 10), (7, 50, 3, 7, 3)])
+def test_ingestion_matches_oracle_aggregation(cuda, shape):
+    g = syn.make_camera_network(3, *shape, outlier_frac=0.1)
+    a = _arrays(g)
+    dg = _device_graph(g, a)
+    pc, pt, B, av = _oracle_pairs(g, a)
+    assert dg.n_edges == pc.shape[0]
+    # oracle pairs are in first-occurrence order; device pairs are sorted by (time, cam)
+    order = np.lexsort((pc, pt))
+    assert np.array_equal(dg.t_cam.cpu().numpy(), pc[order])
+    assert np.array_equal(dg.t_time.cpu().numpy(), pt[order])
+    assert np.abs(dg.t_B.cpu().numpy().reshape(-1, 3, 3) - B[order]).max() < 1e-13
+    assert np.abs(dg.t_a.cpu().numpy() - av[order]).max() < 1e-13
+    rp = dg.t_rowptr.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == dg.n_edges and np.all(np.diff(rp) == np.bincount(pt, minlength=a["n_t"]))
+    cp = dg.c_colptr.cpu().numpy()
+    assert np.all(np.diff(cp) == np.bincount(pc, minlength=a["n_c"]))
+    cperm = dg.c_perm.cpu().numpy()
+    assert np.array_equal(dg.c_time.cpu().numpy(), pt[order][cperm])
+    assert np.array_equal(dg.c_B.cpu().numpy(), dg.t_B.cpu().numpy()[cperm])
+    deg_t = np.zeros(a["n_t"]); np.add.at(deg_t, pt, av)
+    deg_c = np.zeros(a["n_c"]); np.add.at(deg_c, pc, av)
+    assert np.abs(dg.deg_t.cpu().numpy() - deg_t).max() < 1e-12
+    assert np.abs(dg.deg_c.cpu().numpy() - deg_c).max() < 1e-11
+    # tiles cover every camera-sorted edge exactly once, one camera per tile
+    nt = dg.n_tiles
+    tc, ts, te = (x.cpu().numpy()[:nt] for x in (dg.tile_cam, dg.tile_start, dg.tile_end))
+    assert np.all(te > ts) and np.all(te - ts <= dg.tile_len)
+    assert ts[0] == 0 and te[-1] == dg.n_edges and np.all(ts[1:] == te[:-1])
+    assert np.all(cp[tc] <= ts) and np.all(te <= cp[tc + 1])
+
+
+@pytest.mark.parametrize("shape,tile_len", [((12, 80, 4, 4, 2), None), ((30, 400, 6, 11, 2), 24), ((25, 200, 5, 25, 2), 48)])
+def test_edge_passes_match_numpy(cuda, shape, tile_len):
+    from vican_b200.solver import _ptr, _stream
+    g = syn.make_camera_network(4, *shape)
+    a = _arrays(g)
+    dg = _device_graph(g, a, tile_len=tile_len)
+    pc, pt, B, av = _oracle_pairs(g, a)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((a["n_c"], 3, 3))
+    lamT = rng.standard_normal((a["n_t"], 3, 3))
+    Z0 = dm.pass_time(pc, pt, B, X, a["n_t"])
+    W0 = lamT @ Z0
+    Y0 = dm.pass_cam(pc, pt, B, W0, a["n_c"])
+    Xd = torch.as_tensor(X.reshape(-1, 9)).cuda()
+    Ld = torch.as_tensor(lamT.reshape(-1, 9)).cuda()
+    out = torch.empty((a["n_t"], 9), dtype=torch.float64, device="cuda")
+    assert cuda.vb_pass_time(C.byref(dg.cgraph), 1, _ptr(Xd), None, _ptr(out), _stream()) == 0
+    assert np.abs(out.cpu().numpy().reshape(-1, 3, 3) - Z0).max() < 1e-12 * np.abs(Z0).max()
+    assert cuda.vb_pass_time(C.byref(dg.cgraph), 0, _ptr(Xd), _ptr(Ld), _ptr(out), _stream()) == 0
+    assert np.abs(out.cpu().numpy().reshape(-1, 3, 3) - W0).max() < 1e-12 * np.abs(W0).max()
+    Y = torch.zeros((a["n_c"], 9), dtype=torch.float64, device="cuda")
+    assert cuda.vb_pass_cam(C.byref(dg.cgraph), _ptr(out), _ptr(Y), _stream()) == 0
+    assert np.abs(Y.cpu().numpy().reshape(-1, 3, 3) - Y0).max() < 1e-12 * np.abs(Y0).max()
+
+
+# ------------------------------------------------------------------------ rotation stage
+@pytest.mark.parametrize("seed,shape,maxiter,outl,filt", [
+    (5, (12, 80, 4, 4, 2), 1, 0.0, True), (5, (12, 80, 4, 4, 2), 2, 0.0, True), (5, (12, 80, 4, 4, 2), 3, 0.0, True),
+    (6, (12, 80, 4, 4, 2), 10, 0.0, True), (1, (20, 300, 6, 7, 3), 4, 0.0, True),
+    (8, (15, 120, 6, 5, 3), 5, 0.2, True), (9, (15, 120, 6, 5, 3), 5, 0.1, False),
+    (11, (200, 1500, 24, 20, 10), 6, 0.0, True), (4, (600, 6000, 1, 40, 1), 4, 0.0, True),
+    (2, (3, 30, 2, 3, 2), 3, 0.0, True)])
+def test_rotation_stage_matches_oracle(cuda, seed, shape, maxiter, outl, filt):
+    from vican_b200.solver import solve_rotations
+    g = syn.make_camera_network(seed, *shape, outlier_frac=outl, cube=(shape[2] == 24))
+    a = _arrays(g, filt)
+    dg = _device_graph(g, a)
+    pc, pt, B, av = _oracle_pairs(g, a)
+    r_c0, r_t0 = orc.so3sync(pc, pt, B, av, a["n_c"], a["n_t"], maxiter)
+    rot = solve_rotations(dg, maxiter)
+    assert rot.status == 0, rot.status
+    r_c = rot.r_c.cpu().numpy().reshape(-1, 3, 3)
+    r_t = rot.r_t.cpu().numpy().reshape(-1, 3, 3)
+    ec, et = geodesic_rad(r_c, r_c0).max(), geodesic_rad(r_t, r_t0).max()
+    assert ec <= ROT_TOL_RAD and et <= ROT_TOL_RAD, (ec, et, list(rot.stats.inner_per_outer[:maxiter]))
+    # much tighter in practice: the eigen-solve is converged to 1e-11 relative
+    assert ec <= 1e-8 and et <= 1e-8, (ec, et)
+    assert rot.stats.time_passes > 0 and rot.stats.cam_passes > 0
+
+
+# ------------------------------------------------------------------------------ full API
+@pytest.mark.parametrize("name", golden_names())
+def test_api_matches_reference_golden(cuda, name):
+    from vican_b200.bipgo import bipartite_se3sync, object_bipartite_se3sync
+    g, params, filter_on, ref = load_golden(name)
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(filter_on)
+    if g.kind == "object":
+        out = object_bipartite_se3sync(edges, nr, nt, ef, dtype=np.float64, **params)
+    else:
+        out = bipartite_se3sync(edges, constraints, nr, nt, ef, dtype=np.float64, **params)
+    rot, tr = compare(out, ref)
+    assert rot <= ROT_TOL_RAD, rot
+    assert tr <= TRANS_REL_TOL, tr
+
+
+@pytest.mark.parametrize("cfg,scale,solver", [("cfg1", 0.2, "direct"), ("cfg1", 0.2, "conjugate_gradient"),
+                                               ("cfg2", 0.25, "conjugate_gradient"), ("cfg2", 0.1, "direct"),
+                                               ("cfg3", 0.03, "conjugate_gradient")])
+def test_api_matches_oracle_on_baseline_shapes(cuda, cfg, scale, solver):
+    """BASELINE.json config shapes (scaled so the oracle finishes in seconds)."""
+    from vican_b200 import bipgo
+    g, p = syn.make_config(cfg, scale)
+    p["lsqr_solver"] = solver
+    p["maxiter"] = min(p["maxiter"], 6)
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(True)
+    if g.kind == "object":
+        out = bipgo.object_bipartite_se3sync(edges, nr, nt, ef, dtype=np.float64, **p)
+        ref, info = orc.object_bipartite_se3sync_oracle(edges, nr, nt, ef, se3_cls=SE3, return_info=True, **p)
+    else:
+        out = bipgo.bipartite_se3sync(edges, constraints, nr, nt, ef, dtype=np.float64, **p)
+        ref, info = orc.bipartite_se3sync_oracle(edges, constraints, nr, nt, ef, return_info=True, **p)
+    rot, tr = compare(out, ref)
+    assert rot <= ROT_TOL_RAD and tr <= TRANS_REL_TOL, (rot, tr, bipgo.last_info)
+    if solver == "direct":
+        assert bipgo.last_info["trans_iters"] == info["itn"] and bipgo.last_info["trans_istop"] == info["istop"]
+
+
+def test_cg_replays_scipy_iteration_count(cuda):
+    """The device CG must stop at the same iteration as scipy's cg (rtol=1e-5 before each step)."""
+    import scipy.sparse.linalg as spl
+    from vican_b200 import bipgo
+    g = syn.make_camera_network(21, 25, 400, 6, 6, 3)
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(True)
+    count = {"n": 0}
+    orig = orc._scipy_cg
+
+    def counting_cg(A, b, **kw):
+        def cb(xk):
+            count["n"] += 1
+        return spl.cg(A, b, callback=cb, **kw)
+    orc._scipy_cg = counting_cg
+    try:
+        ref = orc.bipartite_se3sync_oracle(edges, constraints, nr, nt, ef, 4, "conjugate_gradient")
+    finally:
+        orc._scipy_cg = orig
+    out = bipgo.bipartite_se3sync(edges, constraints, nr, nt, ef, 4, "conjugate_gradient", dtype=np.float64)
+    assert bipgo.last_info["trans_iters"] == count["n"], (bipgo.last_info["trans_iters"], count["n"])
+    rot, tr = compare(out, ref)
+    assert rot <= ROT_TOL_RAD and tr <= TRANS_REL_TOL
+
+
+def test_output_contract(cuda):
+    """Keys, container type, dtypes and gauge as the reference returns them."""
+    from vican_b200.bipgo import bipartite_se3sync, large_bipartite_so3sync
+    g = syn.make_camera_network(13, 12, 40, 3, 4, 2)
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(True)
+    out = bipartite_se3sync(edges, constraints, nr, nt, ef, 3, "conjugate_gradient")
+    cams = {k[0] for k in edges}
+    times = {k[1].split("_")[0] + "_0" for k in edges}
+    assert set(out.keys()) == cams | times
+    assert list(out.keys()) == sorted(out.keys())
+    v = out[sorted(cams)[0]]
+    assert isinstance(v, SE3) and v.R().dtype == np.float32 and v.t().dtype == np.float64
+    assert v.inv().R().dtype == np.float32 and (v @ v.inv()).R().shape == (3, 3)
+    rots = large_bipartite_so3sync(edges, constraints, nr, ef, 3, dtype=np.float64)
+    assert set(rots.keys()) == set(out.keys())
+    # gauge: the first camera (lexicographic) is the identity up to the primal/dual updates
+    with pytest.raises(ValueError):
+        bipartite_se3sync(edges, constraints, nr, nt, ef, 3, "cholesky")
+    bad = dict(edges)
+    k0 = next(iter(bad))
+    bad[(k0[0], k0[1].split("_")[0] + "_99")] = bad[k0]
+    with pytest.raises(KeyError):
+        bipartite_se3sync(bad, constraints, nr, nt, ef, 3, "conjugate_gradient")
+
+
+def test_accurate_mode_is_close_to_exact_minimiser(cuda):
+    """mode='accurate' (Jacobi-PCG to 1e-12) vs a dense least-squares solve of the same system."""
+    from vican_b200 import bipgo
+    g = syn.make_camera_network(17, 10, 60, 3, 4, 2)
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(True)
+    out = bipgo.bipartite_se3sync(edges, constraints, nr, nt, ef, 4, "conjugate_gradient", dtype=np.float64,
+                                  mode="accurate")
+    # exact min-norm solution from the oracle's J, t~ (same rotations to 1e-11)
+    ref, info = orc.bipartite_se3sync_oracle(edges, constraints, nr, nt, ef, 4, "conjugate_gradient", return_info=True)
+    keys = sorted(ref.keys())
+    t_acc = np.stack([out[k].t() for k in keys])
+    t_ref = np.stack([ref[k][1] for k in keys])
+    # reference CG is only 1e-5-accurate; the accurate mode differs from it by the truncation error
+    assert rel_translation_err(t_acc, t_ref).max() < 5e-2
+    # and has zero mean (minimum-norm gauge of the singular normal equations)
+    assert np.abs(t_acc.mean(axis=0)).max() < 1e-8 * np.abs(t_acc).max()

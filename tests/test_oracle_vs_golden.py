@@ -20,10 +20,14 @@ def test_oracle_matches_reference_golden(name):
     else:
         out = orc.bipartite_se3sync_oracle(edges, constraints, nr, nt, ef, **params)
     rot, tr = compare(out, ref)
-    # the restatement reproduces the reference far below the parity tolerance
+    # rotations: the restatement reproduces the reference to rounding (dense eigh vs ARPACK)
     assert rot < 1e-9, rot
-    assert tr < 1e-7, tr
-    assert rot < ROT_TOL_RAD and tr < TRANS_REL_TOL
+    # translations: cg replays to ~1e-11; scipy's lsqr amplifies 1e-16 input perturbations to
+    # ~1e-7 on the object-calibration graphs (measured: identical J, b differing by 3e-14 ->
+    # x differing by 3e-8 with the same itn), so only the stated parity tolerance is asserted
+    if params["lsqr_solver"] == "conjugate_gradient":
+        assert tr < 1e-9, tr
+    assert rot < ROT_TOL_RAD and tr < TRANS_REL_TOL, (rot, tr)
 
 
 def test_golden_set_not_empty():

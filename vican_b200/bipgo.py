@@ -1,0 +1,191 @@
+"""Drop-in replacements for the reference's solver entry points.
+
+    from vican_b200.bipgo import bipartite_se3sync, object_bipartite_se3sync
+
+keep the signatures and result conventions of ``vican/bipgo.py:353-490`` and ``:493-545``
+(``src_edges`` dict, ``constraints``, ``noise_model_r`` / ``noise_model_t`` / ``edge_filter``
+callables, ``maxiter``, ``lsqr_solver``, ``dtype``) and run the numerics on the GPU through
+the C ABI (``include/vican_b200.h``).  The Python callables necessarily run on the host, once
+per detection, while the dictionary is flattened into arrays; nothing else does.
+"""
+from __future__ import annotations
+
+import time as _time
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import solver as _solver
+from .geometry import SE3
+
+__all__ = ["bipartite_se3sync", "object_bipartite_se3sync", "large_bipartite_so3sync", "EdgeTable", "last_info"]
+
+# diagnostics of the most recent call (iteration counts, Ritz values, timings)
+last_info: Dict[str, object] = {}
+
+
+class EdgeTable:
+    """Flattened detections: what the reference keeps in Python dicts (bipgo.py:203-221,
+    :420-431) as arrays, with node indices in the reference's lexicographic node order."""
+
+    def __init__(self, src_edges: dict, constraints: dict, noise_model_r: Callable, noise_model_t: Callable,
+                 edge_filter: Callable):
+        self.root = str(min(list(constraints.keys())))                       # bipgo.py:411 (string min)
+        cams, times, marks, Rs, ts, kr, kt = [], [], [], [], [], [], []
+        for key, v in src_edges.items():
+            if not edge_filter(v):                                           # bipgo.py:204 / :423
+                continue
+            tstamp, marker_id = key[1].split("_")                            # bipgo.py:206-207
+            constraints[marker_id]                                           # KeyError like bipgo.py:209
+            pose = v["pose"]
+            cams.append(key[0])
+            times.append(tstamp)
+            marks.append(marker_id)
+            Rs.append(pose.R())
+            ts.append(pose.t())
+            kr.append(noise_model_r(v))                                      # bipgo.py:212
+            kt.append(noise_model_t(v))                                      # bipgo.py:449
+        if not cams:
+            raise ValueError("no edge passes edge_filter")
+        self.n_raw = len(cams)
+        # node order = np.unique over 'c'+id / 't'+timestamp strings (bipgo.py:225-229); the
+        # one-letter prefix does not change the order, so unique over the bare ids is the same
+        self.cam_ids, cam_idx = np.unique(np.asarray(cams), return_inverse=True)
+        self.time_ids, time_idx = np.unique(np.asarray(times), return_inverse=True)
+        self.marker_ids = sorted(set(marks) | {self.root})
+        mpos = {m: i for i, m in enumerate(self.marker_ids)}
+        self.cam_idx = cam_idx.astype(np.int32)
+        self.time_idx = time_idx.astype(np.int32)
+        self.marker_idx = np.fromiter((mpos[m] for m in marks), dtype=np.int32, count=self.n_raw)
+        R = np.stack(Rs)
+        # numpy evaluates `k_r * pose.R()` in float32 when the pose arrays are float32 (poses
+        # that went through SE3.inv(), geometry.py:209-211) and k_r is a Python float
+        self.round_kr_f32 = bool(R.dtype == np.float32 and not isinstance(kr[0], np.floating))
+        self.R = R.astype(np.float64).reshape(-1, 9)
+        self.t = np.stack(ts).astype(np.float64).reshape(-1, 3)
+        self.k_r = np.asarray(kr, dtype=np.float64)
+        self.k_t = np.asarray(kt, dtype=np.float64)
+        # per-marker constants (<= a few dozen): same numpy expressions as the reference
+        R0 = np.asarray(constraints[self.root].R())
+        self.markerC = np.stack([np.asarray(constraints[m].R(), dtype=np.float64).T @ R0.astype(np.float64)
+                                 for m in self.marker_ids])                  # R_m^T R_0, bipgo.py:213
+        q = []
+        for m in self.marker_ids:
+            r_0m = constraints[self.root].R().T @ constraints[m].R()         # bipgo.py:451
+            t_m0 = (constraints[m].inv() @ constraints[self.root]).t()       # bipgo.py:452 (float32 arithmetic)
+            q.append(np.asarray(r_0m, dtype=np.float64) @ np.asarray(t_m0, dtype=np.float64))
+        self.marker_q = np.stack(q)
+
+    @property
+    def n_c(self) -> int:
+        return int(self.cam_ids.shape[0])
+
+    @property
+    def n_t(self) -> int:
+        return int(self.time_ids.shape[0])
+
+
+def _solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: Optional[str], mode: str = "parity",
+                 tol: float = 1e-11):
+    t0 = _time.perf_counter()
+    g = _solver.DeviceGraph(tab.cam_idx, tab.time_idx, tab.marker_idx, tab.R, tab.k_r, tab.k_t, tab.markerC,
+                            tab.n_c, tab.n_t, round_kr_f32=tab.round_kr_f32)
+    rot = _solver.solve_rotations(g, maxiter, tol=tol)
+    tr = None
+    if lsqr_solver is not None:
+        tr = _solver.solve_translations(g, rot, tab.t, tab.marker_q, lsqr_solver, mode=mode)
+    torch.cuda.synchronize()
+    last_info.clear()
+    last_info.update(dict(
+        n_c=g.n_c, n_t=g.n_t, n_edges=g.n_edges, n_raw=g.n_raw, n_tiles=g.n_tiles,
+        inner_per_outer=list(rot.stats.inner_per_outer[:min(maxiter, 64)]),
+        time_passes=rot.stats.time_passes, cam_passes=rot.stats.cam_passes,
+        theta=list(rot.stats.theta), resid=list(rot.stats.resid), eig_status=rot.status,
+        trans_iters=None if tr is None else tr.iters, trans_istop=None if tr is None else tr.istop,
+        device_seconds=_time.perf_counter() - t0))
+    return g, rot, tr
+
+
+def large_bipartite_so3sync(src_edges: dict, constraints: dict, noise_model: Callable, edge_filter: Callable,
+                            maxiter: int, dtype=np.float32) -> dict:
+    """Rotation stage only (vican/bipgo.py:145-350): {camera id: R, f"{t}_0": R} wrt the world."""
+    tab = EdgeTable(src_edges, constraints, noise_model, lambda e: 1.0, edge_filter)
+    _, rot, _ = _solve_table(tab, maxiter, None)
+    Rc, Rt = rot.world_rotations()
+    Rc, Rt = Rc.cpu().numpy().astype(dtype), Rt.cpu().numpy().astype(dtype)
+    out = {}
+    for i, c in enumerate(tab.cam_ids):                                      # bipgo.py:344-348
+        out[c] = Rc[i]
+    for j, t in enumerate(tab.time_ids):
+        out[t + "_0"] = Rt[j]
+    return out
+
+
+def bipartite_se3sync(src_edges: dict, constraints: dict, noise_model_r: Callable, noise_model_t: Callable,
+                      edge_filter: Callable, maxiter: int, lsqr_solver: str, dtype=np.float32,
+                      *, mode: str = "parity") -> dict:
+    """SE(3) synchronisation in a bipartite camera / object-timestep graph with node
+    constraints; same contract as ``vican/bipgo.py:353-490``.  Returns a dict with every camera
+    id and every ``f"{t}_0"`` node mapped to an ``SE3`` pose wrt the world.
+
+    The arithmetic is always fp64 on the device; ``dtype`` only selects the dtype of the returned
+    rotation arrays (the reference's ``R`` follows ``dtype``, its ``t`` is float64).
+    Raises ``ValueError`` for an unknown ``lsqr_solver`` (the reference falls through to a
+    NameError) and ``ConvergenceError`` (an ``AssertionError``) if CG does not converge."""
+    if lsqr_solver not in ("conjugate_gradient", "direct"):
+        raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
+    tab = EdgeTable(src_edges, constraints, noise_model_r, noise_model_t, edge_filter)
+    _, rot, tr = _solve_table(tab, maxiter, lsqr_solver, mode=mode)
+    Rc, Rt = rot.world_rotations()
+    Rc, Rt = Rc.cpu().numpy().astype(dtype), Rt.cpu().numpy().astype(dtype)
+    xc, xt = tr.x_c.cpu().numpy(), tr.x_t.cpu().numpy()
+    # result order = np.unique over camera ids and t+'_0' (bipgo.py:420-430, :484-487)
+    cam_keys = list(tab.cam_ids)
+    time_keys = [t + "_0" for t in tab.time_ids]
+    names = np.asarray(cam_keys + time_keys)
+    order = np.argsort(names, kind="stable")
+    Rall = np.concatenate([Rc, Rt], axis=0)
+    tall = np.concatenate([xc, xt], axis=0)
+    out = {}
+    for i in order:
+        out[names[i]] = SE3(R=Rall[i], t=tall[i])
+    return out
+
+
+def object_bipartite_se3sync(src_edges: dict, noise_model_r: Callable, noise_model_t: Callable,
+                             edge_filter: Callable, maxiter: int, lsqr_solver: str, dtype=np.float32,
+                             *, mode: str = "parity") -> dict:
+    """Object calibration (single object, moving camera); same contract as
+    ``vican/bipgo.py:493-545``: markers take the camera role, timesteps the object role, every
+    pose is inverted (through float32, as ``SE3.inv`` does) and only marker poses are returned."""
+    root = str(min([int(k[1].split("_")[1]) for k in src_edges.keys()]))      # bipgo.py:524 (numeric min)
+    # bipgo.py:526-531: re-key and invert every pose.  SE3.inv() stores its result in a float32
+    # 4x4 (geometry.py:239-243); fp64 poses are inverted as one device batch with the same
+    # rounding, float32 poses keep numpy's float32 arithmetic via the container itself.
+    keys = list(src_edges.keys())
+    vals = [src_edges[k] for k in keys]
+    R0 = np.asarray(vals[0]["pose"].R()) if vals else None
+    if vals and R0.dtype == np.float64:
+        from . import ops
+        Ri, ti = ops.se3_invert_batch(np.stack([v["pose"].R() for v in vals]),
+                                      np.stack([np.asarray(v["pose"].t(), dtype=np.float64) for v in vals]),
+                                      round_f32=True)
+        P4 = np.zeros((len(vals), 4, 4), dtype=np.float32)
+        P4[:, :3, :3] = Ri.cpu().numpy()
+        P4[:, :3, 3] = ti.cpu().numpy()
+        P4[:, 3, 3] = 1.0
+        inv_poses = [SE3(pose=P4[i]) for i in range(len(vals))]
+    else:
+        inv_poses = [v["pose"].inv() for v in vals]
+    edges = {}
+    for k, v, ip in zip(keys, vals, inv_poses):
+        t, marker_id = k[1].split("_")
+        edges[marker_id, t + "_" + root] = {"pose": ip,
+                                            "corners": v["corners"],
+                                            "reprojected_err": v["reprojected_err"],
+                                            "im_filename": v["im_filename"]}
+    out = bipartite_se3sync(edges, constraints={root: SE3(pose=np.eye(4))}, noise_model_r=noise_model_r,
+                            noise_model_t=noise_model_t, edge_filter=edge_filter, maxiter=maxiter,
+                            lsqr_solver=lsqr_solver, dtype=dtype, mode=mode)
+    return {k: v for k, v in out.items() if "_" not in k}                    # bipgo.py:543

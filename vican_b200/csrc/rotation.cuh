@@ -1,0 +1,238 @@
+// Rotation stage: per-node SVD kernels and the primal-dual loop driver
+// (replaces vican/bipgo.py:271-348; one thread per node, registers only).
+#pragma once
+#include "../../include/vican_b200.h"
+#include "common.cuh"
+#include "lobpcg.cuh"
+#include "passes.cuh"
+
+namespace vb {
+
+constexpr int NODE_THREADS = 128;
+
+inline int node_grid(int64_t n) { return (int)((n + NODE_THREADS - 1) / NODE_THREADS); }
+
+// bipgo.py:271-276: Lambda_T = I / deg_t, Lambda_C = pwr_deg I with pwr_deg_c = sum_t a_ct.
+__global__ void init_lambda_kernel(const double* __restrict__ deg, double* __restrict__ lam, double* __restrict__ lam_inv,
+                                   int64_t n, int invert) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = deg[i];
+    const double v = invert ? 1.0 / d : d;
+    double* L = lam + 9 * i;
+    L[0] = v; L[1] = 0; L[2] = 0; L[3] = 0; L[4] = v; L[5] = 0; L[6] = 0; L[7] = 0; L[8] = v;
+    if (lam_inv) {
+        const double w = invert ? d : 1.0 / d;
+        double* Li = lam_inv + 9 * i;
+        Li[0] = w; Li[1] = 0; Li[2] = 0; Li[3] = 0; Li[4] = w; Li[5] = 0; Li[6] = 0; Li[7] = 0; Li[8] = w;
+    }
+}
+
+__global__ void fill_identity_kernel(double* __restrict__ X, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* L = X + 9 * i;
+    L[0] = 1; L[1] = 0; L[2] = 0; L[3] = 0; L[4] = 1; L[5] = 0; L[6] = 0; L[7] = 0; L[8] = 1;
+}
+
+// bipgo.py:295-297: r_c = project_SO3(V_c inv(V_0)); camera 0 is the gauge camera (first in the
+// reference's lexicographic node order -- the host assigns indices in that order).
+__global__ void __launch_bounds__(NODE_THREADS) gauge_project_kernel(const double* __restrict__ V, double* __restrict__ r_c, int64_t n_c) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_c) return;
+    double v0[9], v0i[9], v[9], x[9], rot[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { v0[i] = V[i]; v[i] = V[9 * c + i]; }
+    inv3(v0, v0i);
+    mm3(v, v0i, x);
+    svd3_factors(x, rot, nullptr, nullptr);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r_c[9 * c + i] = rot[i];
+}
+
+// bipgo.py:306-315
+__global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const double* __restrict__ M, double* __restrict__ r_c, double* __restrict__ lamC,
+                                     double* __restrict__ lamCinv, int64_t n_c) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_c) return;
+    double m[9], rot[9], sp[9], si[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = M[9 * c + i];
+    svd3_factors(m, rot, sp, si);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        r_c[9 * c + i] = rot[i];
+        lamC[9 * c + i] = sp[i];
+        if (lamCinv) lamCinv[9 * c + i] = si[i];
+    }
+}
+
+// bipgo.py:323-332 (+ Wt = Lambda_T Y_t, the time half of the next L-apply; Yt may alias Wt)
+__global__ void __launch_bounds__(NODE_THREADS) dual_update_kernel(const double* Yt, double* __restrict__ r_t, double* __restrict__ lamT, double* Wt,
+                                   int64_t n_t) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_t) return;
+    double y[9], rot[9], si[9], w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) y[i] = Yt[9 * t + i];
+    svd3_factors(y, rot, nullptr, si);
+    mm3(si, y, w);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        r_t[9 * t + i] = rot[i];
+        lamT[9 * t + i] = si[i];
+        if (Wt) Wt[9 * t + i] = w[i];
+    }
+}
+
+__global__ void polar_batch_kernel(const double* __restrict__ M, double* __restrict__ R, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double m[9], rot[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = M[9 * i + k];
+    svd3_factors(m, rot, nullptr, nullptr);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[9 * i + k] = rot[k];
+}
+
+__global__ void svd_factors_batch_kernel(const double* __restrict__ M, double* rot, double* sp, double* si, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double m[9], a[9], b[9], c[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = M[9 * i + k];
+    svd3_factors(m, a, b, c);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (rot) rot[9 * i + k] = a[k];
+        if (sp) sp[9 * i + k] = b[k];
+        if (si) si[9 * i + k] = c[k];
+    }
+}
+
+// ----------------------------------------------------------------------------- workspace
+inline int64_t align256(int64_t b) { return (b + 255) & ~(int64_t)255; }
+
+struct So3Work {
+    double *X, *AX, *W, *AW, *P, *AP, *Y, *lamC, *lamCinv, *degc, *lamT, *Wt, *small, *partial;
+    int64_t bytes;
+};
+
+inline So3Work carve_so3(void* base, int64_t n_c, int64_t n_t) {
+    So3Work w;
+    char* p = (char*)base;
+    int64_t off = 0;
+    auto take = [&](int64_t nd) {
+        double* r = (double*)(p + off);
+        off += align256(nd * (int64_t)sizeof(double));
+        return r;
+    };
+    w.X = take(9 * n_c); w.AX = take(9 * n_c); w.W = take(9 * n_c); w.AW = take(9 * n_c);
+    w.P = take(9 * n_c); w.AP = take(9 * n_c); w.Y = take(9 * n_c);
+    w.lamC = take(9 * n_c); w.lamCinv = take(9 * n_c); w.degc = take(n_c);
+    w.lamT = take(9 * n_t); w.Wt = take(9 * n_t);
+    w.small = take(SM_SIZE);
+    w.partial = take(3 * (int64_t)1024 * LOB_NRED);
+    w.bytes = off;
+    return w;
+}
+
+struct PinnedStatus {
+    double* h = nullptr;
+    PinnedStatus() { cudaMallocHost((void**)&h, SM_SIZE * sizeof(double)); }
+};
+inline double* pinned_status() {
+    static thread_local PinnedStatus s;
+    return s.h;
+}
+
+inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, double* r_t, void* workspace,
+                       int64_t workspace_bytes, vb_so3_stats* stats, cudaStream_t st) {
+    const int64_t n_c = g->n_c, n_t = g->n_t;
+    if (n_c < 3 || opt->maxiter < 1) return VB_STATUS_BAD_ARGUMENT;
+    So3Work w = carve_so3(workspace, n_c, n_t);
+    if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
+    vb_so3_stats local;
+    vb_so3_stats* S = stats ? stats : &local;
+    memset(S, 0, sizeof(*S));
+    double* hs = pinned_status();
+    const size_t cbytes = 9 * n_c * sizeof(double);
+    int status = VB_STATUS_OK;
+
+    auto time_pass = [&](int mode, const double* X, double* out) -> int {
+        S->time_passes++; S->kernel_launches++;
+        return launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, X, w.lamT, out, n_t, st);
+    };
+    auto cam_pass = [&](const double* Wt, double* Y) -> int {
+        VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
+        S->cam_passes++; S->kernel_launches++;
+        int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->tile_end, g->c_time, g->c_B, Wt, Y, g->n_tiles, st);
+        if (rc) return rc;
+        if (opt->allreduce) return opt->allreduce(opt->allreduce_ctx, Y, 9 * n_c, (void*)st);
+        return 0;
+    };
+#define VB_RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+    // initial duals (global camera degree on edge-sharded runs)
+    VB_CHECK(cudaMemcpyAsync(w.degc, g->deg_c, n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (opt->allreduce) VB_RC(opt->allreduce(opt->allreduce_ctx, w.degc, n_c, (void*)st));
+    init_lambda_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.degc, w.lamC, w.lamCinv, n_c, 0);
+    if (n_t > 0) init_lambda_kernel<<<node_grid(n_t), NODE_THREADS, 0, st>>>(g->deg_t, w.lamT, nullptr, n_t, 1);
+    fill_identity_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, n_c);
+    VB_KERNEL_CHECK();
+    S->kernel_launches += 3;
+
+    LobpcgParams lp;
+    lp.n_c = (int)n_c;
+    lp.X = w.X; lp.AX = w.AX; lp.W = w.W; lp.AW = w.AW; lp.P = w.P; lp.AP = w.AP;
+    lp.Y = w.Y; lp.lamC = w.lamC; lp.lamCinv = w.lamCinv; lp.small = w.small; lp.partial = w.partial;
+    lp.tol = opt->tol;
+    const int max_inner = opt->max_inner > 0 ? opt->max_inner : 200;
+
+    for (int outer = 0; outer < opt->maxiter; ++outer) {
+        if (outer == 0) VB_RC(time_pass(0, w.X, w.Wt));
+        VB_RC(cam_pass(w.Wt, w.Y));
+        VB_CHECK(cudaMemsetAsync(w.W, 0, cbytes, st));
+        VB_CHECK(cudaMemsetAsync(w.AW, 0, cbytes, st));
+        VB_CHECK(cudaMemsetAsync(w.P, 0, cbytes, st));
+        VB_CHECK(cudaMemsetAsync(w.AP, 0, cbytes, st));
+        lp.first = 1;
+        VB_RC(launch_lobpcg_step(lp, st));
+        S->lobpcg_steps++; S->kernel_launches++;
+        int inner = 1;
+        for (;;) {
+            VB_CHECK(cudaMemcpyAsync(hs, w.small, SM_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+            VB_CHECK(cudaStreamSynchronize(st));
+            if (hs[SM_CONV] != 0.0) break;
+            if (inner >= max_inner) { S->stalled_outer++; status = VB_STATUS_EIG_STALLED; break; }
+            VB_RC(time_pass(0, w.W, w.Wt));
+            VB_RC(cam_pass(w.Wt, w.Y));
+            lp.first = 0;
+            VB_RC(launch_lobpcg_step(lp, st));
+            S->lobpcg_steps++; S->kernel_launches++;
+            ++inner;
+        }
+        if (outer < 64) S->inner_per_outer[outer] = inner;
+        for (int j = 0; j < 3; ++j) { S->theta[j] = hs[SM_THETA + j]; S->resid[j] = hs[SM_RESN + j]; }
+        S->anorm = hs[SM_ANORM];
+
+        gauge_project_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, r_c, n_c);
+        VB_KERNEL_CHECK();
+        VB_RC(time_pass(0, r_c, w.Wt));
+        VB_RC(cam_pass(w.Wt, w.Y));
+        primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, w.lamC, w.lamCinv, n_c);
+        VB_KERNEL_CHECK();
+        VB_RC(time_pass(1, r_c, w.Wt));
+        if (n_t > 0) dual_update_kernel<<<node_grid(n_t), NODE_THREADS, 0, st>>>(w.Wt, r_t, w.lamT, w.Wt, n_t);
+        VB_KERNEL_CHECK();
+        S->kernel_launches += 3;
+        VB_CHECK(cudaMemcpyAsync(w.X, r_c, cbytes, cudaMemcpyDeviceToDevice, st));
+        S->outer_done = outer + 1;
+    }
+    VB_CHECK(cudaStreamSynchronize(st));
+    return status;
+#undef VB_RC
+}
+
+}  // namespace vb

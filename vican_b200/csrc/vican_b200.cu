@@ -1,0 +1,331 @@
+// C ABI of the vican_b200 CUDA extension (see include/vican_b200.h).  sm_100a only.
+#include "../../include/vican_b200.h"
+
+#include "common.cuh"
+#include "ingest.cuh"
+#include "lobpcg.cuh"
+#include "lsqr.cuh"
+#include "nccl_shim.cuh"
+#include "passes.cuh"
+#include "rotation.cuh"
+#include "translation.cuh"
+
+using namespace vb;
+
+namespace {
+
+__global__ void se3_compose_kernel(const double* __restrict__ Ra, const double* __restrict__ ta, const double* __restrict__ Rb,
+                                   const double* __restrict__ tb, double* __restrict__ Ro, double* __restrict__ to, int64_t n,
+                                   int round_f32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double A[9], B[9], C[9], a[3], b[3], c[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { A[k] = Ra[9 * i + k]; B[k] = Rb[9 * i + k]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a[k] = ta[3 * i + k]; b[k] = tb[3 * i + k]; }
+    if (round_f32) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { A[k] = (double)(float)A[k]; B[k] = (double)(float)B[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { a[k] = (double)(float)a[k]; b[k] = (double)(float)b[k]; }
+    }
+    mm3(A, B, C);
+    mv3(A, b, c);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ro[9 * i + k] = round_f32 ? (double)(float)C[k] : C[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double v = c[k] + a[k]; to[3 * i + k] = round_f32 ? (double)(float)v : v; }
+}
+
+__global__ void se3_invert_kernel(const double* __restrict__ R, const double* __restrict__ t, double* __restrict__ Ri,
+                                  double* __restrict__ ti, int64_t n, int round_f32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double A[9], a[3], c[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A[k] = R[9 * i + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a[k] = t[3 * i + k];
+    mtv3(A, a, c);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double v = A[3 * k + r];
+            Ri[9 * i + 3 * r + k] = round_f32 ? (double)(float)v : v;
+        }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double v = -c[k]; ti[3 * i + k] = round_f32 ? (double)(float)v : v; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vb_version(void) { return "vican_b200 0.1.0 (sm_100a)"; }
+
+const char* vb_status_string(int code) {
+    if (code < 0) return cudaGetErrorString((cudaError_t)(-code));
+    switch (code) {
+        case VB_STATUS_OK: return "ok";
+        case VB_STATUS_NOT_CONVERGED: return "conjugate gradient did not converge";
+        case VB_STATUS_EIG_STALLED: return "eigen-iteration hit max_inner before reaching tol";
+        case VB_STATUS_BAD_ARGUMENT: return "bad argument / workspace too small";
+        default: return "unknown status";
+    }
+}
+
+int vb_se3_compose_batch(const double* Ra, const double* ta, const double* Rb, const double* tb, double* Rout,
+                         double* tout, int64_t n, int round_f32, void* stream) {
+    if (n <= 0) return 0;
+    se3_compose_kernel<<<node_grid(n), NODE_THREADS, 0, (cudaStream_t)stream>>>(Ra, ta, Rb, tb, Rout, tout, n, round_f32);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int vb_se3_invert_batch(const double* R, const double* t, double* Rinv, double* tinv, int64_t n, int round_f32,
+                        void* stream) {
+    if (n <= 0) return 0;
+    se3_invert_kernel<<<node_grid(n), NODE_THREADS, 0, (cudaStream_t)stream>>>(R, t, Rinv, tinv, n, round_f32);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int vb_polar_so3_batch(const double* M, double* R, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    polar_batch_kernel<<<node_grid(n), NODE_THREADS, 0, (cudaStream_t)stream>>>(M, R, n);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int vb_svd3_factors_batch(const double* M, double* rot, double* sym_pos, double* sym_inv, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    svd_factors_batch_kernel<<<node_grid(n), NODE_THREADS, 0, (cudaStream_t)stream>>>(M, rot, sym_pos, sym_inv, n);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ ingestion
+int64_t vb_ingest_workspace_bytes(int64_t n_raw) {
+    IngestWork w = carve_ingest(nullptr, n_raw < 1 ? 1 : n_raw);
+    return w.bytes;
+}
+
+int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64_t n_c, int64_t n_t, int32_t* raw_perm,
+                   int32_t* raw_pair, int64_t* h_n_pairs, void* workspace, int64_t workspace_bytes, void* stream) {
+    return ingest_sort(cam, time, n_raw, n_c, n_t, raw_perm, raw_pair, h_n_pairs, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
+int64_t vb_ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len) {
+    return ingest_max_tiles(n_edges, n_c, tile_len);
+}
+
+int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* marker, const double* R, const double* k_r,
+                    const double* k_t, const double* markerC, int64_t n_raw, int round_kr_f32, const int32_t* raw_perm,
+                    const int32_t* raw_pair, int64_t n_pairs, int64_t n_c, int64_t n_t, int64_t tile_len,
+                    int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
+                    int32_t* pair_start, int32_t* c_colptr, int32_t* c_time, double* c_B, double* c_w, int32_t* c_perm,
+                    int32_t* tile_cam, int32_t* tile_start, int32_t* tile_end, int64_t* h_n_tiles, double* deg_t,
+                    double* deg_c, void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_raw <= 0 || n_pairs <= 0 || tile_len <= 0) return VB_STATUS_BAD_ARGUMENT;
+    IngestWork w = carve_ingest(workspace, n_raw);
+    if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
+    const int64_t E = n_pairs;
+    pair_start_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(raw_pair, pair_start, n_raw, E);
+    fold_aggregate_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(cam, time, marker, R, k_r, k_t, markerC, round_kr_f32,
+                                                              raw_perm, pair_start, E, t_cam, t_time, t_B, t_a, t_w);
+    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_time, nullptr, t_rowptr, E, n_t);
+    seg_sum_kernel<<<ing_grid(n_t * 32), ING_THREADS, 0, st>>>(t_rowptr, nullptr, t_a, deg_t, n_t);
+    VB_KERNEL_CHECK();
+    // camera-sorted copy
+    make_keys_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, t_time, n_t, w.keys_a, w.vals_a, E);
+    size_t tb = w.cub_bytes;
+    VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
+                                             c_perm, (int)E, 0, key_bits(n_c, n_t), st));
+    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, c_perm, c_colptr, E, n_c);
+    gather_cam_sorted_kernel<<<ing_grid(9 * E), ING_THREADS, 0, st>>>(c_perm, t_time, t_B, t_w, c_time, c_B, c_w, E);
+    seg_sum_kernel<<<ing_grid(n_c * 32), ING_THREADS, 0, st>>>(c_colptr, c_perm, t_a, deg_c, n_c);
+    VB_KERNEL_CHECK();
+    // camera tiles
+    tile_count_kernel<<<ing_grid(n_c), ING_THREADS, 0, st>>>(c_colptr, w.tmp_a, n_c, (int)tile_len);
+    tb = w.cub_bytes;
+    VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.tmp_a, w.tmp_b, (int)n_c, st));
+    tile_fill_kernel<<<ing_grid(n_c), ING_THREADS, 0, st>>>(c_colptr, w.tmp_b, tile_cam, tile_start, tile_end, n_c, (int)tile_len);
+    VB_KERNEL_CHECK();
+    int last_off = 0, last_cnt = 0;
+    VB_CHECK(cudaMemcpyAsync(&last_off, w.tmp_b + (n_c - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    VB_CHECK(cudaMemcpyAsync(&last_cnt, w.tmp_a + (n_c - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    VB_CHECK(cudaStreamSynchronize(st));
+    *h_n_tiles = (int64_t)last_off + last_cnt;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- rotation
+int vb_pass_time(const vb_graph* g, int mode, const double* X, const double* lamT, double* out, void* stream) {
+    return launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, X, lamT, out, g->n_t, (cudaStream_t)stream);
+}
+
+int vb_pass_cam(const vb_graph* g, const double* W, double* Y, void* stream) {
+    return launch_pass_cam(g->tile_cam, g->tile_start, g->tile_end, g->c_time, g->c_B, W, Y, g->n_tiles,
+                           (cudaStream_t)stream);
+}
+
+int vb_primal_update(const double* M, double* r_c, double* lamC, double* lamCinv, int64_t n_c, void* stream) {
+    if (n_c <= 0) return 0;
+    primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, (cudaStream_t)stream>>>(M, r_c, lamC, lamCinv, n_c);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int vb_dual_update(const double* Yt, double* r_t, double* lamT, double* Wt, int64_t n_t, void* stream) {
+    if (n_t <= 0) return 0;
+    dual_update_kernel<<<node_grid(n_t), NODE_THREADS, 0, (cudaStream_t)stream>>>(Yt, r_t, lamT, Wt, n_t);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int vb_gauge_project(const double* V, double* r_c, int64_t n_c, void* stream) {
+    if (n_c <= 0) return 0;
+    gauge_project_kernel<<<node_grid(n_c), NODE_THREADS, 0, (cudaStream_t)stream>>>(V, r_c, n_c);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int64_t vb_so3sync_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_so3(nullptr, n_c, n_t).bytes; }
+
+int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, double* r_t, void* workspace,
+                   int64_t workspace_bytes, vb_so3_stats* stats, void* stream) {
+    return so3sync_run(g, opt, r_c, r_t, workspace, workspace_bytes, stats, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------- translation
+int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
+                 const double* t_cm, const double* k_t, const double* marker_q, const double* r_c, const double* r_t,
+                 const int32_t* t_time, const int32_t* c_perm, double* pair_g, double* d_sorted, double* rhs_c,
+                 double* rhs_t, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t E = g->n_edges;
+    if (E <= 0) return VB_STATUS_BAD_ARGUMENT;
+    trans_pair_kernel<<<tr_grid(E), TR_THREADS, 0, st>>>(raw_perm, pair_start, marker, t_cm, k_t, marker_q, r_c, r_t,
+                                                        g->t_cam, t_time, E, pair_g, d_sorted);
+    VB_CHECK(cudaMemsetAsync(rhs_c, 0, 3 * g->n_c * sizeof(double), st));
+    VB_CHECK(cudaMemsetAsync(rhs_t, 0, 3 * g->n_t * sizeof(double), st));
+    seg_sum3_kernel<<<tr_warp_grid(g->n_t), TR_THREADS, 0, st>>>(g->t_rowptr, nullptr, pair_g, 1.0, rhs_t, g->n_t);
+    seg_sum3_kernel<<<tr_warp_grid(g->n_c), TR_THREADS, 0, st>>>(g->c_colptr, c_perm, pair_g, -1.0, rhs_c, g->n_c);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_cg(nullptr, n_c, n_t).bytes; }
+
+int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t, double rtol,
+                int64_t maxiter, int jacobi, int32_t* h_iters, void* workspace, int64_t workspace_bytes,
+                vb_allreduce_fn allreduce, void* allreduce_ctx, void* stream) {
+    return trans_cg(g, rhs_c, rhs_t, x_c, x_t, rtol, maxiter, jacobi, h_iters, workspace, workspace_bytes, allreduce,
+                    allreduce_ctx, (cudaStream_t)stream);
+}
+
+int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw) {
+    return carve_lsqr(nullptr, n_c, n_t, n_raw).bytes;
+}
+
+int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw_pair, const int32_t* pair_start,
+                  const int32_t* t_time, const double* k_t, const double* d_sorted, int64_t n_raw, double* x_c,
+                  double* x_t, double atol, double btol, double conlim, int64_t iter_lim, int32_t* h_istop,
+                  int32_t* h_iters, void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_c = g->n_c, n_t = g->n_t;
+    LsqrWork w = carve_lsqr(workspace, n_c, n_t, n_raw);
+    if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
+    double* hs = pinned_status();
+    lsqr_clear_kernel<<<1, 1, 0, st>>>(w.sc);
+    lsqr_rows_kernel<<<tr_grid(n_raw), TR_THREADS, 0, st>>>(raw_perm, raw_pair, g->t_cam, t_time, k_t, d_sorted, n_raw,
+                                                           w.row_cam, w.row_time, w.kt_sorted, w.u, w.keys_a, w.vals_a);
+    VB_KERNEL_CHECK();
+    size_t tb = w.cub_bytes;
+    int cbits = 1;
+    while (cbits < 64 && ((uint64_t)n_c >> cbits) != 0) ++cbits;
+    VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
+                                             w.cam_rows, (int)n_raw, 0, cbits, st));
+    seg_ptr_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(w.row_cam, w.cam_rows, w.cam_ptr, n_raw, n_c);
+    VB_KERNEL_CHECK();
+    const int nb_u = sumsq_grid(3 * n_raw), nb_c = sumsq_grid(3 * n_c), nb_t = sumsq_grid(3 * n_t);
+    auto v_step = [&](int init) -> int {
+        lsqr_vt_kernel<<<tr_warp_grid(n_t), TR_THREADS, 0, st>>>(g->t_rowptr, pair_start, w.kt_sorted, w.u, w.v_t, n_t, w.sc, init);
+        lsqr_vc_kernel<<<tr_warp_grid(n_c), TR_THREADS, 0, st>>>(w.cam_ptr, w.cam_rows, w.kt_sorted, w.u, w.v_c, n_c, w.sc, init);
+        sumsq_partial_kernel<<<nb_c, TR_THREADS, 0, st>>>(w.v_c, 3 * n_c, 1.0, w.partial);
+        sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.v_t, 3 * n_t, 1.0, w.partial + 1024);
+        lsqr_s2_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_c, nb_t, init);
+        VB_KERNEL_CHECK();
+        return 0;
+    };
+    // initial bidiagonalisation vectors (lsqr.py:372-398)
+    sumsq_partial_kernel<<<nb_u, TR_THREADS, 0, st>>>(w.u, 3 * n_raw, 1.0, w.partial);
+    lsqr_s1_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_u, 1);
+    { int rc = v_step(1); if (rc) return rc; }
+    lsqr_x_kernel<<<tr_grid(3 * n_c), TR_THREADS, 0, st>>>(w.v_c, w.w_c, x_c, 3 * n_c, w.sc, 1);
+    lsqr_x_kernel<<<tr_grid(3 * n_t), TR_THREADS, 0, st>>>(w.v_t, w.w_t, x_t, 3 * n_t, w.sc, 1);
+    VB_KERNEL_CHECK();
+    for (int64_t it = 0; it < iter_lim; ++it) {
+        lsqr_u_kernel<<<tr_grid(n_raw), TR_THREADS, 0, st>>>(w.row_cam, w.row_time, w.kt_sorted, w.v_c, w.v_t, w.u, n_raw, w.sc);
+        sumsq_partial_kernel<<<nb_u, TR_THREADS, 0, st>>>(w.u, 3 * n_raw, 1.0, w.partial);
+        lsqr_s1_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_u, 0);
+        { int rc = v_step(0); if (rc) return rc; }
+        sumsq_partial_kernel<<<nb_c, TR_THREADS, 0, st>>>(w.w_c, 3 * n_c, 1.0, w.partial);
+        sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.w_t, 3 * n_t, 1.0, w.partial + 1024);
+        lsqr_x_kernel<<<tr_grid(3 * n_c), TR_THREADS, 0, st>>>(w.v_c, w.w_c, x_c, 3 * n_c, w.sc, 0);
+        lsqr_x_kernel<<<tr_grid(3 * n_t), TR_THREADS, 0, st>>>(w.v_t, w.w_t, x_t, 3 * n_t, w.sc, 0);
+        lsqr_s3_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_c, nb_t, atol, btol, conlim, (double)iter_lim);
+        VB_KERNEL_CHECK();
+        VB_CHECK(cudaMemcpyAsync(hs, w.sc, LS_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, st));
+        VB_CHECK(cudaStreamSynchronize(st));
+        if (hs[LS_ISTOP] != 0.0) break;
+    }
+    VB_CHECK(cudaMemcpyAsync(hs, w.sc, LS_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VB_CHECK(cudaStreamSynchronize(st));
+    if (h_istop) *h_istop = (int32_t)hs[LS_ISTOP];
+    if (h_iters) *h_iters = (int32_t)hs[LS_ITN];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ multi-GPU
+int vb_nccl_available(void) { return nccl_api().ok ? 1 : 0; }
+
+int vb_nccl_unique_id(void* h_out, int64_t bytes) {
+    if (!nccl_api().ok || bytes < (int64_t)sizeof(ncclUniqueId)) return VB_STATUS_BAD_ARGUMENT;
+    ncclUniqueId id;
+    if (nccl_api().GetUniqueId(&id) != ncclSuccess) return VB_STATUS_BAD_ARGUMENT;
+    memcpy(h_out, &id, sizeof(id));
+    return 0;
+}
+
+int vb_nccl_init(const void* h_id, int64_t bytes, int rank, int nranks, void** ctx_out) {
+    if (!nccl_api().ok || bytes < (int64_t)sizeof(ncclUniqueId)) return VB_STATUS_BAD_ARGUMENT;
+    ncclUniqueId id;
+    memcpy(&id, h_id, sizeof(id));
+    NcclCtx* ctx = new NcclCtx{nullptr, rank, nranks};
+    if (nccl_api().CommInitRank(&ctx->comm, nranks, id, rank) != ncclSuccess) { delete ctx; return VB_STATUS_BAD_ARGUMENT; }
+    *ctx_out = ctx;
+    return 0;
+}
+
+int vb_nccl_destroy(void* ctx) {
+    if (!ctx) return 0;
+    NcclCtx* c = (NcclCtx*)ctx;
+    nccl_api().CommDestroy(c->comm);
+    delete c;
+    return 0;
+}
+
+int vb_nccl_allreduce(void* ctx, double* buf, int64_t count, void* stream) {
+    NcclCtx* c = (NcclCtx*)ctx;
+    ncclResult_t r = nccl_api().AllReduce(buf, buf, (size_t)count, ncclDouble, ncclSum, c->comm, (cudaStream_t)stream);
+    return r == ncclSuccess ? 0 : VB_STATUS_BAD_ARGUMENT;
+}
+
+void* vb_nccl_allreduce_fn(void) { return (void*)&vb_nccl_allreduce; }
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""Array-level device solver: the path BASELINE.json's north_star names, on raw arrays.
+
+``DeviceGraph`` owns the device-resident block-CSR/CSC built by the ingestion kernels;
+``solve_rotations`` runs the primal-dual loop (vican/bipgo.py:145-350) and
+``solve_translations`` the least-squares stage (bipgo.py:420-487).  Everything numerical
+happens in ``libvican_b200.so``; torch only owns memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import VbGraph, VbSo3Options, VbSo3Stats, check
+
+F64 = torch.float64
+I32 = torch.int32
+
+
+class ConvergenceError(AssertionError, RuntimeError):
+    """CG did not converge (the reference trips ``assert exit_code == 0``, bipgo.py:478)."""
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(x, dtype, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device, non_blocking=True)
+
+
+@dataclasses.dataclass
+class Comm:
+    """NCCL communicator handle of the extension (edge-sharded multi-GPU runs)."""
+    ctx: int
+    rank: int
+    world: int
+
+
+def default_tile_len(n_edges: int, n_sms: int = 148) -> int:
+    """Camera-tile length: a multiple of 24 edges (one index chunk), sized so the camera pass
+    has a few thousand warps but at most ~400 edges per 9 fp64 atomics."""
+    tl = (n_edges // (n_sms * 32)) // 24 * 24
+    return int(min(max(tl, 24), 384))
+
+
+class DeviceGraph:
+    """Device-resident aggregated bipartite graph (time-sorted CSR + camera-sorted CSC)."""
+
+    def __init__(self, cam, time, marker, R, k_r, k_t, markerC, n_c: int, n_t: int,
+                 round_kr_f32: bool = False, device=None, tile_len: Optional[int] = None):
+        lib = _cabi.lib()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        self.n_c, self.n_t = int(n_c), int(n_t)
+        self.cam = _dev(cam, I32, dev)
+        self.time = _dev(time, I32, dev)
+        self.marker = _dev(marker, I32, dev)
+        R = _dev(R, F64, dev).reshape(-1, 9)
+        self.k_r = _dev(k_r, F64, dev)
+        self.k_t = _dev(k_t, F64, dev)
+        markerC = _dev(markerC, F64, dev).reshape(-1, 9)
+        n_raw = int(self.cam.shape[0])
+        if n_raw == 0:
+            raise ValueError("no edges survive edge_filter")
+        self.n_raw = n_raw
+        with torch.cuda.device(dev):
+            wsb = int(lib.vb_ingest_workspace_bytes(n_raw))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            self.raw_perm = torch.empty(n_raw, dtype=I32, device=dev)
+            self.raw_pair = torch.empty(n_raw, dtype=I32, device=dev)
+            npairs = C.c_int64(0)
+            check(lib.vb_ingest_sort(_ptr(self.cam), _ptr(self.time), n_raw, self.n_c, self.n_t, _ptr(self.raw_perm),
+                                     _ptr(self.raw_pair), C.byref(npairs), _ptr(ws), wsb, _stream()), "vb_ingest_sort")
+            E = int(npairs.value)
+            self.n_edges = E
+            tl = default_tile_len(E) if tile_len is None else int(tile_len)
+            self.tile_len = tl
+            max_tiles = int(lib.vb_ingest_max_tiles(E, self.n_c, tl))
+            e = lambda n, dt: torch.empty(n, dtype=dt, device=dev)  # noqa: E731
+            self.t_rowptr, self.t_cam, self.t_time = e(self.n_t + 1, I32), e(E, I32), e(E, I32)
+            self.t_B, self.t_a, self.t_w = e((E, 9), F64), e(E, F64), e(E, F64)
+            self.pair_start = e(E + 1, I32)
+            self.c_colptr, self.c_time = e(self.n_c + 1, I32), e(E, I32)
+            self.c_B, self.c_w, self.c_perm = e((E, 9), F64), e(E, F64), e(E, I32)
+            self.tile_cam, self.tile_start, self.tile_end = e(max_tiles, I32), e(max_tiles, I32), e(max_tiles, I32)
+            self.deg_t, self.deg_c = e(self.n_t, F64), e(self.n_c, F64)
+            ntiles = C.c_int64(0)
+            check(lib.vb_ingest_build(
+                _ptr(self.cam), _ptr(self.time), _ptr(self.marker), _ptr(R), _ptr(self.k_r), _ptr(self.k_t),
+                _ptr(markerC), n_raw, 1 if round_kr_f32 else 0, _ptr(self.raw_perm), _ptr(self.raw_pair), E,
+                self.n_c, self.n_t, tl, _ptr(self.t_rowptr), _ptr(self.t_cam), _ptr(self.t_time), _ptr(self.t_B),
+                _ptr(self.t_a), _ptr(self.t_w), _ptr(self.pair_start), _ptr(self.c_colptr), _ptr(self.c_time),
+                _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_perm), _ptr(self.tile_cam), _ptr(self.tile_start),
+                _ptr(self.tile_end), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c), _ptr(ws), wsb, _stream()),
+                "vb_ingest_build")
+            self.n_tiles = int(ntiles.value)
+        del ws, R
+        self.cgraph = VbGraph(
+            self.n_c, self.n_t, E, self.n_tiles,
+            self.t_rowptr.data_ptr(), self.t_cam.data_ptr(), self.t_B.data_ptr(), self.t_w.data_ptr(),
+            self.c_colptr.data_ptr(), self.c_time.data_ptr(), self.c_B.data_ptr(), self.c_w.data_ptr(),
+            self.tile_cam.data_ptr(), self.tile_start.data_ptr(), self.tile_end.data_ptr(),
+            self.deg_t.data_ptr(), self.deg_c.data_ptr())
+
+    # ---- algorithmic bytes of one edge pass (76 B / edge + node traffic) ----
+    def pass_bytes(self, kind: str) -> int:
+        E, n_c, n_t = self.n_edges, self.n_c, self.n_t
+        if kind == "time":     # blocks + cam index, row pointers, Lambda_T read, W write, X gather source
+            return 76 * E + 4 * (n_t + 1) + 72 * n_t + 72 * n_t + 72 * n_c
+        if kind == "cam":      # blocks + time index, tile table, W gather source, Y accumulate
+            return 76 * E + 12 * self.n_tiles + 72 * n_t + 2 * 72 * n_c
+        raise ValueError(kind)
+
+
+@dataclasses.dataclass
+class RotationResult:
+    r_c: torch.Tensor           # [n_c, 9] as stored by the reference before its final transpose
+    r_t: torch.Tensor           # [n_t, 9]
+    stats: VbSo3Stats
+    status: int
+
+    def world_rotations(self):
+        """bipgo.py:344-348: out = r^T."""
+        return (self.r_c.view(-1, 3, 3).transpose(1, 2).contiguous(),
+                self.r_t.view(-1, 3, 3).transpose(1, 2).contiguous())
+
+
+def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-11, max_inner: int = 200,
+                    comm: Optional[Comm] = None) -> RotationResult:
+    lib = _cabi.lib()
+    dev = g.device
+    with torch.cuda.device(dev):
+        wsb = int(lib.vb_so3sync_workspace_bytes(g.n_c, g.n_t))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        r_c = torch.empty((g.n_c, 9), dtype=F64, device=dev)
+        r_t = torch.empty((g.n_t, 9), dtype=F64, device=dev)
+        opt = VbSo3Options(int(maxiter), int(max_inner), float(tol),
+                           lib.vb_nccl_allreduce_fn() if comm is not None else None,
+                           comm.ctx if comm is not None else None)
+        stats = VbSo3Stats()
+        rc = lib.vb_so3sync_run(C.byref(g.cgraph), C.byref(opt), _ptr(r_c), _ptr(r_t), _ptr(ws), wsb,
+                                C.byref(stats), _stream())
+        check(rc, "vb_so3sync_run", allow=(2,))
+    return RotationResult(r_c, r_t, stats, rc)
+
+
+@dataclasses.dataclass
+class TranslationResult:
+    x_c: torch.Tensor           # [n_c, 3]
+    x_t: torch.Tensor           # [n_t, 3]
+    iters: int
+    istop: int
+
+
+def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr_solver: str,
+                       mode: str = "parity", comm: Optional[Comm] = None) -> TranslationResult:
+    """``lsqr_solver``: "conjugate_gradient" | "direct" (reference names, bipgo.py:476-480).
+    ``mode``: "parity" replays scipy's truncated iterations (what the reference returns);
+    "accurate" runs Jacobi-preconditioned CG to 1e-12 (closer to the true minimiser, and
+    therefore up to ~4e-3 away from the reference's CG answer -- SURVEY.md 7.3-1)."""
+    if lsqr_solver not in ("conjugate_gradient", "direct"):
+        raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
+    lib = _cabi.lib()
+    dev = g.device
+    with torch.cuda.device(dev):
+        t_cm = _dev(t_cm, F64, dev).reshape(-1, 3)
+        marker_q = _dev(marker_q, F64, dev).reshape(-1, 3)
+        E = g.n_edges
+        pair_g = torch.empty((E, 3), dtype=F64, device=dev)
+        need_rows = (lsqr_solver == "direct" and mode == "parity")
+        d_sorted = torch.empty((g.n_raw, 3), dtype=F64, device=dev) if need_rows else None
+        rhs_c = torch.empty((g.n_c, 3), dtype=F64, device=dev)
+        rhs_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
+        check(lib.vb_trans_rhs(C.byref(g.cgraph), _ptr(g.raw_perm), _ptr(g.pair_start), _ptr(g.marker), _ptr(t_cm),
+                               _ptr(g.k_t), _ptr(marker_q), _ptr(rot.r_c), _ptr(rot.r_t), _ptr(g.t_time),
+                               _ptr(g.c_perm), _ptr(pair_g), _ptr(d_sorted), _ptr(rhs_c), _ptr(rhs_t), _stream()),
+              "vb_trans_rhs")
+        x_c = torch.empty((g.n_c, 3), dtype=F64, device=dev)
+        x_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
+        iters = C.c_int32(0)
+        istop = C.c_int32(0)
+        if need_rows:
+            if comm is not None:
+                raise NotImplementedError("lsqr_solver='direct' is the small-graph path (single GPU)")
+            wsb = int(lib.vb_trans_lsqr_workspace_bytes(g.n_c, g.n_t, g.n_raw))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            n_unknowns = 3 * (g.n_c + g.n_t)
+            check(lib.vb_trans_lsqr(C.byref(g.cgraph), _ptr(g.raw_perm), _ptr(g.raw_pair), _ptr(g.pair_start),
+                                    _ptr(g.t_time), _ptr(g.k_t), _ptr(d_sorted), g.n_raw, _ptr(x_c), _ptr(x_t),
+                                    1e-6, 1e-6, 1e8, 2 * n_unknowns, C.byref(istop), C.byref(iters), _ptr(ws), wsb,
+                                    _stream()), "vb_trans_lsqr")
+        else:
+            if comm is not None and rhs_c is not None:
+                # camera rows of J^T t~ are partial sums over the local edge shard
+                check(lib.vb_nccl_allreduce(comm.ctx, _ptr(rhs_c), 3 * g.n_c, _stream()), "vb_nccl_allreduce")
+            wsb = int(lib.vb_trans_cg_workspace_bytes(g.n_c, g.n_t))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            n_unknowns = 3 * (g.n_c + g.n_t)   # global count differs on shards; only the cap depends on it
+            jacobi = 1 if mode == "accurate" else 0
+            rtol = 1e-12 if mode == "accurate" else 1e-5
+            rc = lib.vb_trans_cg(C.byref(g.cgraph), _ptr(rhs_c), _ptr(rhs_t), _ptr(x_c), _ptr(x_t), rtol,
+                                 10 * n_unknowns, jacobi, C.byref(iters), _ptr(ws), wsb,
+                                 lib.vb_nccl_allreduce_fn() if comm is not None else None,
+                                 comm.ctx if comm is not None else None, _stream())
+            if rc == 1:
+                raise ConvergenceError("conjugate gradient did not converge (reference: assert exit_code == 0)")
+            check(rc, "vb_trans_cg")
+            if jacobi:
+                # J^T J is singular (global translation).  Plain CG from x0 = 0 stays orthogonal to the
+                # null space (minimum-norm solution, what the reference returns); the preconditioned
+                # iteration does not, so remove the mean explicitly (3 numbers; plumbing, not a kernel).
+                tot = torch.cat([x_c.sum(0) , x_t.sum(0), torch.tensor([float(g.n_t)], dtype=F64, device=dev)])
+                if comm is not None:
+                    tot[:3] = 0.0  # camera block is replicated: count it once, below
+                    check(lib.vb_nccl_allreduce(comm.ctx, _ptr(tot), 7, _stream()), "vb_nccl_allreduce")
+                    tot[:3] = x_c.sum(0)
+                mean = (tot[:3] + tot[3:6]) / (g.n_c + tot[6])
+                x_c -= mean
+                x_t -= mean
+    return TranslationResult(x_c, x_t, int(iters.value), int(istop.value))
