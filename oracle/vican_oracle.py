@@ -240,3 +240,21 @@ def object_bipartite_se3sync_oracle(src_edges, noise_model_r, noise_model_t, edg
     out, info = res if return_info else (res, None)
     out = {k: v for k, v in out.items() if "_" not in k}                              # :543
     return (out, info) if return_info else out
+
+
+# ------------------------------------------------------------------ array front-end
+def solve_arrays_oracle(cam, time, marker, R, t, k_r, k_t, marker_R, marker_t_inv0, root, n_c, n_t, maxiter,
+                        lsqr_solver):
+    """Whole path on pre-indexed arrays (used by bench.py's CPU baseline and the large-shape
+    tests): bipgo.py:203-348 + :434-487 without the dictionaries.  Unknown order is
+    [cameras; time nodes].  Returns (Rw_c, Rw_t, x_c, x_t)."""
+    blk = fold_blocks(R, k_r, marker, marker_R, root)
+    pc, pt, B, a = aggregate_pairs(cam, time, blk, k_r, n_t)
+    r_c, r_t = so3sync(pc, pt, B, a, n_c, n_t, maxiter)
+    Rw_c = np.transpose(r_c, (0, 2, 1))
+    Rw_t = np.transpose(r_t, (0, 2, 1))
+    J, t_tilde = translation_system(cam, time, marker, t, k_t, marker_R, marker_t_inv0, root, Rw_c, Rw_t, n_c, n_t,
+                                    np.arange(n_c), n_c + np.arange(n_t))
+    x, _ = solve_translations(J, t_tilde, lsqr_solver)
+    x = x.reshape(-1, 3)
+    return Rw_c, Rw_t, x[:n_c], x[n_c:]

@@ -229,3 +229,43 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
                 x_c -= mean
                 x_t -= mean
     return TranslationResult(x_c, x_t, int(iters.value), int(istop.value))
+
+
+@dataclasses.dataclass
+class SolveResult:
+    Rw_c: torch.Tensor          # [n_c, 3, 3] world rotations of the cameras
+    Rw_t: torch.Tensor          # [n_t, 3, 3] world rotations of the (local) time nodes
+    x_c: torch.Tensor           # [n_c, 3]
+    x_t: torch.Tensor           # [n_t, 3]
+    graph: DeviceGraph
+    rot: RotationResult
+    trans: TranslationResult
+    phase_ms: dict
+
+
+def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int, n_t: int, maxiter: int,
+                 lsqr_solver: str = "conjugate_gradient", mode: str = "parity", tol: float = 1e-11,
+                 comm: Optional[Comm] = None, round_kr_f32: bool = False, to_host: bool = False,
+                 graph: Optional[DeviceGraph] = None) -> SolveResult:
+    """Array fast path of ``bipartite_se3sync`` (no dicts, no Python callables): raw detections
+    as arrays (numpy / pinned host tensors / CUDA tensors) with pre-evaluated weights
+    ``k_r = noise_model_r(e)``, ``k_t = noise_model_t(e)`` and already filtered by
+    ``edge_filter``; node indices dense and in the caller's order (index 0 = gauge camera).
+    With ``to_host`` the results are copied back to (pinned) host memory."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    g = graph if graph is not None else DeviceGraph(cam, time, marker, R, k_r, k_t, markerC, n_c, n_t,
+                                                     round_kr_f32=round_kr_f32)
+    ev[1].record()
+    rot = solve_rotations(g, maxiter, tol=tol, comm=comm)
+    ev[2].record()
+    tr = solve_translations(g, rot, t, marker_q, lsqr_solver, mode=mode, comm=comm)
+    Rw_c, Rw_t = rot.world_rotations()
+    x_c, x_t = tr.x_c, tr.x_t
+    if to_host:
+        Rw_c, Rw_t, x_c, x_t = (v.to("cpu", non_blocking=False) for v in (Rw_c, Rw_t, x_c, x_t))
+    ev[3].record()
+    torch.cuda.synchronize()
+    phase = dict(ingest=ev[0].elapsed_time(ev[1]), rotation=ev[1].elapsed_time(ev[2]),
+                 translation=ev[2].elapsed_time(ev[3]))
+    return SolveResult(Rw_c, Rw_t, x_c, x_t, g, rot, tr, phase)
