@@ -106,19 +106,26 @@ def test_ingestion_matches_oracle_aggregation(cuda, shape):
     assert rp[0] == 0 and rp[-1] == dg.n_edges and np.all(np.diff(rp) == np.bincount(pt, minlength=a["n_t"]))
     cp = dg.c_colptr.cpu().numpy()
     assert np.all(np.diff(cp) == np.bincount(pc, minlength=a["n_c"]))
-    cperm = dg.c_perm.cpu().numpy()
-    assert np.array_equal(dg.c_time.cpu().numpy(), pt[order][cperm])
-    assert np.array_equal(dg.c_B.cpu().numpy(), dg.t_B.cpu().numpy()[cperm])
+    cperm = dg.c_perm.cpu().numpy()                       # camera-major permutation (per-camera reductions)
+    assert np.array_equal(pc[order][cperm], np.sort(pc)) and sorted(cperm.tolist()) == list(range(dg.n_edges))
+    cord = dg.c_order.cpu().numpy()                       # camera-pass order: (time window, camera, time)
+    assert sorted(cord.tolist()) == list(range(dg.n_edges))
+    assert np.array_equal(dg.c_time.cpu().numpy(), pt[order][cord])
+    assert np.array_equal(dg.c_B.cpu().numpy(), dg.t_B.cpu().numpy()[cord])
+    assert np.array_equal(dg.c_w.cpu().numpy(), dg.t_w.cpu().numpy()[cord])
     deg_t = np.zeros(a["n_t"]); np.add.at(deg_t, pt, av)
     deg_c = np.zeros(a["n_c"]); np.add.at(deg_c, pc, av)
     assert np.abs(dg.deg_t.cpu().numpy() - deg_t).max() < 1e-12
     assert np.abs(dg.deg_c.cpu().numpy() - deg_c).max() < 1e-11
-    # tiles cover every camera-sorted edge exactly once, one camera per tile
+    # tiles cover every camera-pass edge exactly once, one camera per tile, contiguous + sentinel
     nt = dg.n_tiles
     tc, ts, te = (x.cpu().numpy()[:nt] for x in (dg.tile_cam, dg.tile_start, dg.tile_end))
     assert np.all(te > ts) and np.all(te - ts <= dg.tile_len)
     assert ts[0] == 0 and te[-1] == dg.n_edges and np.all(ts[1:] == te[:-1])
-    assert np.all(cp[tc] <= ts) and np.all(te <= cp[tc + 1])
+    assert int(dg.tile_start.cpu().numpy()[nt]) == dg.n_edges
+    cam_of_pos = pc[order][cord]
+    for k in range(nt):
+        assert np.all(cam_of_pos[ts[k]:te[k]] == tc[k])
 
 
 @pytest.mark.parametrize("shape,tile_len", [((12, 80, 4, 4, 2), None), ((30, 400, 6, 11, 2), 24), ((25, 200, 5, 25, 2), 48)])

@@ -32,7 +32,7 @@ class VbGraph(C.Structure):
     _fields_ = [
         ("n_c", I64), ("n_t", I64), ("n_edges", I64), ("n_tiles", I64),
         ("t_rowptr", VP), ("t_cam", VP), ("t_B", VP), ("t_w", VP),
-        ("c_colptr", VP), ("c_time", VP), ("c_B", VP), ("c_w", VP),
+        ("c_colptr", VP), ("c_perm", VP), ("c_time", VP), ("c_B", VP), ("c_w", VP),
         ("tile_cam", VP), ("tile_start", VP), ("tile_end", VP),
         ("deg_t", VP), ("deg_c", VP),
     ]
@@ -62,7 +62,7 @@ SIGNATURES = {
     "vb_ingest_sort": (C.c_int, [VP, VP, I64, I64, I64, VP, VP, c_i64p, VP, I64, VP]),
     "vb_ingest_max_tiles": (I64, [I64, I64, I64]),
     "vb_ingest_build": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, I64, C.c_int, VP, VP, I64, I64, I64, I64,
-                                  VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, c_i64p, VP, VP,
+                                  VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, c_i64p, VP, VP,
                                   VP, I64, VP]),
     "vb_pass_time": (C.c_int, [C.POINTER(VbGraph), C.c_int, VP, VP, VP, VP]),
     "vb_pass_cam": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP]),

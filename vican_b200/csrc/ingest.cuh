@@ -133,21 +133,41 @@ __global__ void tile_count_kernel(const int* __restrict__ colptr, int* __restric
 }
 
 __global__ void tile_fill_kernel(const int* __restrict__ colptr, const int* __restrict__ off, int* __restrict__ tile_cam,
-                                 int* __restrict__ tile_start, int* __restrict__ tile_end, int64_t n_c, int tile_len) {
+                                 int* __restrict__ tile_start, int* __restrict__ tile_end, int64_t n_seg, int64_t n_c,
+                                 int tile_len) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_c) return;
+    if (c >= n_seg) return;
     const int s = colptr[c], e = colptr[c + 1];
     int t = off[c];
     for (int b = s; b < e; b += tile_len, ++t) {
-        tile_cam[t] = (int)c;
+        tile_cam[t] = (int)(c % n_c);
         tile_start[t] = b;
         tile_end[t] = (b + tile_len < e) ? b + tile_len : e;
     }
 }
 
+// key = ((window(time) * n_c + cam) * n_t + time): camera-pass order.  Tiles of all cameras that
+// fall in the same time window are adjacent in the stream, so the W records gathered by
+// concurrently running warps come from one window of W (L2 resident) instead of all of it.
+__global__ void make_window_keys_kernel(const int* __restrict__ cam, const int* __restrict__ time, int64_t n_c, int64_t n_t,
+                                        int64_t n_win, uint64_t* __restrict__ keys, int* __restrict__ vals, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t t = (uint64_t)time[i];
+    const uint64_t win = t * (uint64_t)n_win / (uint64_t)n_t;
+    keys[i] = (win * (uint64_t)n_c + (uint64_t)cam[i]) * (uint64_t)n_t + t;
+    vals[i] = (int)i;
+}
+
+__global__ void window_seg_kernel(const uint64_t* __restrict__ keys_sorted, int64_t n_t, int* __restrict__ seg, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    seg[i] = (int)(keys_sorted[i] / (uint64_t)n_t);
+}
+
 struct IngestWork {
     uint64_t *keys_a, *keys_b;
-    int *vals_a, *tmp_a, *tmp_b;
+    int *vals_a, *tmp_a, *tmp_b, *tmp_c, *tmp_d;
     void* cub_tmp;
     size_t cub_bytes;
     int64_t bytes;
@@ -175,6 +195,8 @@ inline IngestWork carve_ingest(void* base, int64_t n) {
     w.vals_a = (int*)take(4 * n);
     w.tmp_a = (int*)take(4 * (n + 1));
     w.tmp_b = (int*)take(4 * (n + 1));
+    w.tmp_c = (int*)take(4 * (n + 1));
+    w.tmp_d = (int*)take(4 * (n + 1));
     w.cub_bytes = cub_temp_bytes(n);
     w.cub_tmp = take((int64_t)w.cub_bytes);
     w.bytes = off;
@@ -204,8 +226,14 @@ inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n
     return 0;
 }
 
+inline int64_t ingest_windows(int64_t n_edges, int64_t n_c, int64_t tile_len) {
+    const int64_t per_cam = (n_edges + n_c - 1) / n_c;
+    const int64_t w = (per_cam + tile_len - 1) / tile_len;
+    return w < 1 ? 1 : w;
+}
+
 inline int64_t ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len) {
-    return n_edges / tile_len + n_c + 1;
+    return n_edges / tile_len + n_c * ingest_windows(n_edges, n_c, tile_len) + 2;
 }
 
 }  // namespace vb

@@ -114,12 +114,13 @@ __device__ __forceinline__ void block_atomic_sum(double (&v)[N], double* const (
 }
 
 // weighted degrees (diagonal of J^T J): dg_t = sum_row w, dg_c = sum_col w
-__global__ void seg_sum1_kernel(const int* __restrict__ ptr, const double* __restrict__ w, double* __restrict__ out, int64_t n_nodes) {
+__global__ void seg_sum1_kernel(const int* __restrict__ ptr, const int* __restrict__ perm, const double* __restrict__ w,
+                                double* __restrict__ out, int64_t n_nodes) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= n_nodes) return;
     double a = 0;
-    for (int i = ptr[warp] + lane; i < ptr[warp + 1]; i += 32) a += w[i];
+    for (int i = ptr[warp] + lane; i < ptr[warp + 1]; i += 32) a += w[perm ? perm[i] : i];
     a = warp_sum(a);
     if (lane == 0) out[warp] = a;
 }
@@ -274,8 +275,8 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     double* hs = pinned_status();
     VB_CHECK(cudaMemsetAsync(w.sc, 0, CG_NSCAL * sizeof(double), st));
     if (jacobi) {
-        if (n_t > 0) seg_sum1_kernel<<<tr_warp_grid(n_t), TR_THREADS, 0, st>>>(g->t_rowptr, g->t_w, w.dg_t, n_t);
-        seg_sum1_kernel<<<tr_warp_grid(n_c), TR_THREADS, 0, st>>>(g->c_colptr, g->c_w, w.dg_c, n_c);
+        if (n_t > 0) seg_sum1_kernel<<<tr_warp_grid(n_t), TR_THREADS, 0, st>>>(g->t_rowptr, nullptr, g->t_w, w.dg_t, n_t);
+        seg_sum1_kernel<<<tr_warp_grid(n_c), TR_THREADS, 0, st>>>(g->c_colptr, g->c_perm, g->t_w, w.dg_c, n_c);
         if (allreduce) { int rc = allreduce(actx, w.dg_c, n_c, (void*)st); if (rc) return rc; }
     }
     // camera part is replicated across ranks -> counted once on every rank; time part is local

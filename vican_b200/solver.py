@@ -88,12 +88,20 @@ class DeviceGraph:
             self.tile_len = tl
             max_tiles = int(lib.vb_ingest_max_tiles(E, self.n_c, tl))
             e = lambda n, dt: torch.empty(n, dtype=dt, device=dev)  # noqa: E731
-            self.t_rowptr, self.t_cam, self.t_time = e(self.n_t + 1, I32), e(E, I32), e(E, I32)
-            self.t_B, self.t_a, self.t_w = e((E, 9), F64), e(E, F64), e(E, F64)
+            z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
+            # the edge passes stream blocks / indices with 16-byte granular bulk copies:
+            # 2 blocks / 8 indices of zero padding behind the arrays keep those reads in bounds
+            self._t_cam_pad, self._t_B_pad = z(E + 8, I32), z((E + 2, 9), F64)
+            self._c_time_pad, self._c_B_pad = z(E + 8, I32), z((E + 2, 9), F64)
+            self.t_cam, self.t_B = self._t_cam_pad[:E], self._t_B_pad[:E]
+            self.c_time, self.c_B = self._c_time_pad[:E], self._c_B_pad[:E]
+            self.t_rowptr, self.t_time = e(self.n_t + 1, I32), e(E, I32)
+            self.t_a, self.t_w = e(E, F64), e(E, F64)
             self.pair_start = e(E + 1, I32)
-            self.c_colptr, self.c_time = e(self.n_c + 1, I32), e(E, I32)
-            self.c_B, self.c_w, self.c_perm = e((E, 9), F64), e(E, F64), e(E, I32)
-            self.tile_cam, self.tile_start, self.tile_end = e(max_tiles, I32), e(max_tiles, I32), e(max_tiles, I32)
+            self.c_colptr = e(self.n_c + 1, I32)
+            self.c_w, self.c_perm, self.c_order = e(E, F64), e(E, I32), e(E, I32)
+            self.tile_cam, self.tile_start, self.tile_end = (e(max_tiles + 1, I32), e(max_tiles + 1, I32),
+                                                             e(max_tiles + 1, I32))
             self.deg_t, self.deg_c = e(self.n_t, F64), e(self.n_c, F64)
             ntiles = C.c_int64(0)
             check(lib.vb_ingest_build(
@@ -101,7 +109,8 @@ class DeviceGraph:
                 _ptr(markerC), n_raw, 1 if round_kr_f32 else 0, _ptr(self.raw_perm), _ptr(self.raw_pair), E,
                 self.n_c, self.n_t, tl, _ptr(self.t_rowptr), _ptr(self.t_cam), _ptr(self.t_time), _ptr(self.t_B),
                 _ptr(self.t_a), _ptr(self.t_w), _ptr(self.pair_start), _ptr(self.c_colptr), _ptr(self.c_time),
-                _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_perm), _ptr(self.tile_cam), _ptr(self.tile_start),
+                _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_perm), _ptr(self.c_order), _ptr(self.tile_cam),
+                _ptr(self.tile_start),
                 _ptr(self.tile_end), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c), _ptr(ws), wsb, _stream()),
                 "vb_ingest_build")
             self.n_tiles = int(ntiles.value)
@@ -109,7 +118,8 @@ class DeviceGraph:
         self.cgraph = VbGraph(
             self.n_c, self.n_t, E, self.n_tiles,
             self.t_rowptr.data_ptr(), self.t_cam.data_ptr(), self.t_B.data_ptr(), self.t_w.data_ptr(),
-            self.c_colptr.data_ptr(), self.c_time.data_ptr(), self.c_B.data_ptr(), self.c_w.data_ptr(),
+            self.c_colptr.data_ptr(), self.c_perm.data_ptr(), self.c_time.data_ptr(), self.c_B.data_ptr(),
+            self.c_w.data_ptr(),
             self.tile_cam.data_ptr(), self.tile_start.data_ptr(), self.tile_end.data_ptr(),
             self.deg_t.data_ptr(), self.deg_c.data_ptr())
 
