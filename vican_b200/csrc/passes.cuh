@@ -219,6 +219,37 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+// One group of NR rounds (3 edges each) of the current item.  Lane (q, r) multiplies its block
+// entry with one row of the gathered 3x3 block.  It loads ONE entry of that row itself and
+// takes the other two from its two neighbour lanes, accumulating "rotated" partial sums
+// (acc_d belongs to output column (rot + d) mod 3) -- 2 instead of 3 fp64 shuffles per round;
+// the LSU/shuffle return path is what bounds this kernel (profiles/r1_passes_v2.md).
+template <int NR>
+__device__ __forceinline__ void edge_group(const double* __restrict__ sB, const int* __restrict__ sI,
+                                           const double* __restrict__ G, int offB, int offI, int g0, int n_e,
+                                           int q, int r, int gsel, int src1, int src2, uint64_t pl, double& c0,
+                                           double& c1, double& c2) {
+    double bv[NR], xv[NR];
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+        const int off = g0 + 3 * u + q;
+        const bool on = (q < 3) && (off < n_e);
+        bv[u] = 0.0; xv[u] = 0.0;
+        if (on) {
+            const int node = sI[offI + off];
+            bv[u] = sB[9 * (offB + off) + r];
+            xv[u] = ld_keep(G + 9 * (size_t)node + gsel, pl);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+        const double x1 = shfl(xv[u], src1), x2 = shfl(xv[u], src2);
+        c0 = fma(bv[u], xv[u], c0);
+        c1 = fma(bv[u], x1, c1);
+        c2 = fma(bv[u], x2, c2);
+    }
+}
+
 // MODE 0: out_t = Lambda_T[t] * sum B^T X   MODE 1: out_t = sum B^T X   MODE 2: Y_c += sum B W (atomics per tile)
 template <int MODE>
 __global__ void __launch_bounds__(PASS_THREADS, 2)
@@ -243,8 +274,14 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
 
     const uint64_t pf = policy_evict_first(), pl = policy_evict_last();
     const int q = lane / 9, r = lane - 9 * q;
-    const int krow = TR ? (r / 3) : (r % 3);
-    const int src = 9 * q + 3 * krow;
+    // TR : r = 3k + i (block entry B[k][i]),  gathers X[k][i],   row mates = lanes 9q + 3k + *
+    // !TR: r = 3i + k (block entry B[i][k]),  gathers W[k][i],   row mates = lanes 9q + 3* + k
+    const int hi = r / 3, lo = r - 3 * hi;
+    const int rot = TR ? lo : hi;                       // = output row of this lane
+    const int gsel = TR ? r : (3 * lo + hi);
+    const int m1 = (rot + 1) % 3, m2 = (rot + 2) % 3;
+    const int src1 = TR ? (9 * q + 3 * hi + m1) : (9 * q + 3 * m1 + lo);
+    const int src2 = TR ? (9 * q + 3 * hi + m2) : (9 * q + 3 * m2 + lo);
 
     auto issue = [&](int a, int b, int buf) {   // elected lane only
         const int a0 = a & ~1, b1 = (b + 1) & ~1;
@@ -256,11 +293,9 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
         bulk_g2s(dst + BUF_B_BYTES, idx + a0i, nbI, &bars[buf], pf);
     };
 
-    // current segment / item
     int cseg = warp;
     int cs = __ldg(seg_ptr + cseg), ce = __ldg(seg_ptr + cseg + 1);
     int ca = cs, cb = min(cs + ITEM_EDGES, ce);
-    // look-ahead segment (row pointers prefetched one segment early)
     int nseg = cseg + nwarps, ns = 0, ne = 0;
     if (nseg < n_seg) { ns = __ldg(seg_ptr + nseg); ne = __ldg(seg_ptr + nseg + 1); }
     uint32_t phase0 = 0, phase1 = 0;
@@ -270,9 +305,15 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
         if (lane == 0) issue(ca, cb, 0);
         cur_issued = true; cur_buf = 0; n_issued = 1;
     }
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    // Lambda_T row for the epilogue of the current segment, fetched early (latency hidden)
+    double lam0 = 0.0, lam1 = 0.0, lam2 = 0.0;
+    if (MODE == 0 && lane < 3) {
+        const double* L = lamT + 9 * (size_t)cseg + 3 * lane;
+        lam0 = L[0]; lam1 = L[1]; lam2 = L[2];
+    }
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
     for (;;) {
-        // ---- look ahead: the next item is the next chunk of this segment or the head of the next segment
+        // ---- look ahead: next chunk of this segment, or the head of the next segment
         bool has_next = true, next_new_seg = false;
         int na = 0, nb = 0;
         if (cb < ce) { na = cb; nb = min(cb + ITEM_EDGES, ce); }
@@ -287,7 +328,7 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
             next_issued = true;
             ++n_issued;
         }
-        // ---- consume the current item
+        // ---- consume the current item from shared memory
         if (cur_issued) {
             if (cur_buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
             else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
@@ -296,42 +337,29 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
             const int* sI = reinterpret_cast<const int*>(bufp + BUF_B_BYTES);
             const int offB = ca - (ca & ~1), offI = ca - (ca & ~3);
             const int n_e = cb - ca;
-            for (int g0 = 0; g0 < n_e; g0 += 3 * GUNR) {
-                double bv[GUNR], xv[GUNR];
-#pragma unroll
-                for (int u = 0; u < GUNR; ++u) {
-                    const int off = g0 + 3 * u + q;
-                    const bool on = (q < 3) && (off < n_e);
-                    bv[u] = 0.0; xv[u] = 0.0;
-                    if (on) {
-                        const int node = sI[offI + off];
-                        bv[u] = sB[9 * (offB + off) + r];
-                        xv[u] = ld_keep(G + 9 * (size_t)node + r, pl);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < GUNR; ++u) {
-                    const double x0 = shfl(xv[u], src), x1 = shfl(xv[u], src + 1), x2 = shfl(xv[u], src + 2);
-                    a0 = fma(bv[u], x0, a0);
-                    a1 = fma(bv[u], x1, a1);
-                    a2 = fma(bv[u], x2, a2);
-                }
-            }
+            int g0 = 0;
+            for (; g0 + 3 * 8 <= n_e; g0 += 3 * 8) edge_group<8>(sB, sI, G, offB, offI, g0, n_e, q, r, gsel, src1, src2, pl, c0, c1, c2);
+            if (g0 + 3 * 4 <= n_e) { edge_group<4>(sB, sI, G, offB, offI, g0, n_e, q, r, gsel, src1, src2, pl, c0, c1, c2); g0 += 12; }
+            if (g0 + 3 * 2 <= n_e) { edge_group<2>(sB, sI, G, offB, offI, g0, n_e, q, r, gsel, src1, src2, pl, c0, c1, c2); g0 += 6; }
+            if (g0 + 3 <= n_e) { edge_group<1>(sB, sI, G, offB, offI, g0, n_e, q, r, gsel, src1, src2, pl, c0, c1, c2); g0 += 3; }
+            if (g0 < n_e) edge_group<1>(sB, sI, G, offB, offI, g0, n_e, q, r, gsel, src1, src2, pl, c0, c1, c2);
         }
-        // ---- segment finished: reduce and emit
+        // ---- segment finished: reduce (rotated sums share their rotation within a row), un-rotate, emit
         if (cb >= ce) {
-            edge_reduce<TR>(a0, a1, a2);
+            edge_reduce<TR>(c0, c1, c2);
+            // final lanes: TR -> 0,1,2 (rot = lane) ; !TR -> 0,3,6 (rot = lane / 3)
+            const double a0 = (rot == 0) ? c0 : ((rot == 1) ? c2 : c1);
+            const double a1 = (rot == 0) ? c1 : ((rot == 1) ? c0 : c2);
+            const double a2 = (rot == 0) ? c2 : ((rot == 1) ? c1 : c0);
             if (MODE == 0) {
                 double z[9];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { z[3 * i] = shfl(a0, i); z[3 * i + 1] = shfl(a1, i); z[3 * i + 2] = shfl(a2, i); }
                 if (lane < 3) {
-                    const double* L = lamT + 9 * (size_t)cseg + 3 * lane;
-                    const double l0 = L[0], l1 = L[1], l2 = L[2];
                     double* o = out + 9 * (size_t)cseg + 3 * lane;
-                    o[0] = l0 * z[0] + l1 * z[3] + l2 * z[6];
-                    o[1] = l0 * z[1] + l1 * z[4] + l2 * z[7];
-                    o[2] = l0 * z[2] + l1 * z[5] + l2 * z[8];
+                    o[0] = lam0 * z[0] + lam1 * z[3] + lam2 * z[6];
+                    o[1] = lam0 * z[1] + lam1 * z[4] + lam2 * z[7];
+                    o[2] = lam0 * z[2] + lam1 * z[5] + lam2 * z[8];
                 }
             } else if (MODE == 1) {
                 if (lane < 3) { double* o = out + 9 * (size_t)cseg + 3 * lane; o[0] = a0; o[1] = a1; o[2] = a2; }
@@ -341,7 +369,7 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
                     atomicAdd(y, a0); atomicAdd(y + 1, a1); atomicAdd(y + 2, a2);
                 }
             }
-            a0 = 0.0; a1 = 0.0; a2 = 0.0;
+            c0 = 0.0; c1 = 0.0; c2 = 0.0;
         }
         if (!has_next) break;
         // ---- advance
@@ -349,6 +377,10 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
             cseg = nseg; cs = ns; ce = ne;
             nseg += nwarps;
             if (nseg < n_seg) { ns = __ldg(seg_ptr + nseg); ne = __ldg(seg_ptr + nseg + 1); }
+            if (MODE == 0 && lane < 3) {
+                const double* L = lamT + 9 * (size_t)cseg + 3 * lane;
+                lam0 = L[0]; lam1 = L[1]; lam2 = L[2];
+            }
         }
         ca = na; cb = nb; cur_issued = next_issued; cur_buf = next_buf;
     }
