@@ -245,14 +245,14 @@ def main():
 
     # ---- per-kernel roofline: the two edge passes, timed alone with CUDA events (inputs 3.9 GB >> L2)
     import ctypes as C
-    X = torch.randn((n_c, 9), dtype=torch.float64, device=dev)
+    X = torch.randn((n_c, 12), dtype=torch.float64, device=dev)       # padded gather layout (3 rows x 4)
     lamT = torch.randn((g.n_t, 9), dtype=torch.float64, device=dev)
-    Wt = torch.empty((g.n_t, 9), dtype=torch.float64, device=dev)
+    Wt = torch.zeros((g.n_t, 12), dtype=torch.float64, device=dev)
     Y = torch.zeros((n_c, 9), dtype=torch.float64, device=dev)
     ptr, stream = solver._ptr, solver._stream
     kern = {}
-    for name, fn in (("pass_time_kernel<0>", lambda: lib.vb_pass_time(C.byref(g.cgraph), 0, ptr(X), ptr(lamT), ptr(Wt), stream())),
-                     ("pass_cam_kernel", lambda: lib.vb_pass_cam(C.byref(g.cgraph), ptr(Wt), ptr(Y), stream()))):
+    for name, fn in (("edge_pass_kernel<0> (time pass)", lambda: lib.vb_pass_time(C.byref(g.cgraph), 0, ptr(X), ptr(lamT), ptr(Wt), stream())),
+                     ("edge_pass_kernel<2> (camera pass)", lambda: lib.vb_pass_cam(C.byref(g.cgraph), ptr(Wt), ptr(Y), stream()))):
         for _ in range(3):
             fn()
         reps = 20

@@ -128,15 +128,19 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int64_t workspace_bytes, void* stream);
 
 /* ---- rotation stage (bipgo.py:243-348) --------------------------------------------------- */
-/* One edge pass each (exposed for tests and for the roofline measurement):
- *   vb_pass_time: out_t = [Lambda_T[t]] * sum_{e in t} B_e^T X[c_e]   (mode 0 with lamT, mode 1 raw sum)
- *   vb_pass_cam : Y_c  += sum_{e in c} B_e W[t_e]                      (Y must be zeroed by the caller) */
-int vb_pass_time(const vb_graph* g, int mode, const double* X, const double* lamT, double* out, void* stream);
-int vb_pass_cam(const vb_graph* g, const double* W, double* Y, void* stream);
+/* One edge pass each (exposed for tests and for the roofline measurement).  Gathered node
+ * blocks use the PADDED layout [n][12] (3 rows x 4 doubles, row = 32 bytes) so that one row is
+ * one 256-bit load; vb_pad_blocks converts a compact [n][9] array.
+ *   vb_pass_time: out12_t = [Lambda_T[t]] * sum_{e in t} B_e^T X12[c_e]  (mode 0 with lamT [n_t][9], mode 1 raw sum)
+ *   vb_pass_cam : Y_c    += sum_{e in c} B_e W12[t_e]      (Y compact [n_c][9], zeroed by the caller) */
+int vb_pad_blocks(const double* src9, double* dst12, int64_t n, void* stream);
+int vb_pass_time(const vb_graph* g, int mode, const double* X12, const double* lamT, double* out12, void* stream);
+int vb_pass_cam(const vb_graph* g, const double* W12, double* Y, void* stream);
 /* Per-node updates: primal (bipgo.py:306-315): r_c, Lambda_C = U S U^T, Lambda_C^-1;
- * dual (bipgo.py:323-332): r_t, Lambda_T = U S^-1 U^T, and Wt = Lambda_T Y_t. */
+ * dual (bipgo.py:323-332): r_t, Lambda_T = U S^-1 U^T, and Wt12 = Lambda_T Y_t (Yt12 / Wt12 padded,
+ * may alias). */
 int vb_primal_update(const double* M, double* r_c, double* lamC, double* lamCinv, int64_t n_c, void* stream);
-int vb_dual_update(const double* Yt, double* r_t, double* lamT, double* Wt, int64_t n_t, void* stream);
+int vb_dual_update(const double* Yt12, double* r_t, double* lamT, double* Wt12, int64_t n_t, void* stream);
 /* Gauge + projection (bipgo.py:295-297): X_c <- project_SO3(V_c V_0^-1). */
 int vb_gauge_project(const double* V, double* r_c, int64_t n_c, void* stream);
 

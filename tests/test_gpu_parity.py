@@ -128,7 +128,8 @@ def test_ingestion_matches_oracle_aggregation(cuda, shape):
         assert np.all(cam_of_pos[ts[k]:te[k]] == tc[k])
 
 
-@pytest.mark.parametrize("shape,tile_len", [((12, 80, 4, 4, 2), None), ((30, 400, 6, 11, 2), 24), ((25, 200, 5, 25, 2), 48)])
+@pytest.mark.parametrize("shape,tile_len", [((12, 80, 4, 4, 2), None), ((30, 400, 6, 11, 2), 24), ((25, 200, 5, 25, 2), 48),
+                                            ((90, 300, 3, 83, 1), 120), ((40, 30, 2, 37, 2), None)])
 def test_edge_passes_match_numpy(cuda, shape, tile_len):
     from vican_b200.solver import _ptr, _stream
     g = syn.make_camera_network(4, *shape)
@@ -142,12 +143,16 @@ def test_edge_passes_match_numpy(cuda, shape, tile_len):
     W0 = lamT @ Z0
     Y0 = dm.pass_cam(pc, pt, B, W0, a["n_c"])
     Xd = torch.as_tensor(X.reshape(-1, 9)).cuda()
+    X12 = torch.empty((a["n_c"], 12), dtype=torch.float64, device="cuda")
+    assert cuda.vb_pad_blocks(_ptr(Xd), _ptr(X12), a["n_c"], _stream()) == 0
+    assert np.array_equal(X12.cpu().numpy().reshape(-1, 3, 4)[:, :, :3], X)
     Ld = torch.as_tensor(lamT.reshape(-1, 9)).cuda()
-    out = torch.empty((a["n_t"], 9), dtype=torch.float64, device="cuda")
-    assert cuda.vb_pass_time(C.byref(dg.cgraph), 1, _ptr(Xd), None, _ptr(out), _stream()) == 0
-    assert np.abs(out.cpu().numpy().reshape(-1, 3, 3) - Z0).max() < 1e-12 * np.abs(Z0).max()
-    assert cuda.vb_pass_time(C.byref(dg.cgraph), 0, _ptr(Xd), _ptr(Ld), _ptr(out), _stream()) == 0
-    assert np.abs(out.cpu().numpy().reshape(-1, 3, 3) - W0).max() < 1e-12 * np.abs(W0).max()
+    out = torch.zeros((a["n_t"], 12), dtype=torch.float64, device="cuda")
+    unpad = lambda t: t.cpu().numpy().reshape(-1, 3, 4)[:, :, :3]  # noqa: E731
+    assert cuda.vb_pass_time(C.byref(dg.cgraph), 1, _ptr(X12), None, _ptr(out), _stream()) == 0
+    assert np.abs(unpad(out) - Z0).max() < 1e-12 * np.abs(Z0).max()
+    assert cuda.vb_pass_time(C.byref(dg.cgraph), 0, _ptr(X12), _ptr(Ld), _ptr(out), _stream()) == 0
+    assert np.abs(unpad(out) - W0).max() < 1e-12 * np.abs(W0).max()
     Y = torch.zeros((a["n_c"], 9), dtype=torch.float64, device="cuda")
     assert cuda.vb_pass_cam(C.byref(dg.cgraph), _ptr(out), _ptr(Y), _stream()) == 0
     assert np.abs(Y.cpu().numpy().reshape(-1, 3, 3) - Y0).max() < 1e-12 * np.abs(Y0).max()

@@ -67,21 +67,31 @@ __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const doubl
     }
 }
 
-// bipgo.py:323-332 (+ Wt = Lambda_T Y_t, the time half of the next L-apply; Yt may alias Wt)
-__global__ void __launch_bounds__(NODE_THREADS) dual_update_kernel(const double* Yt, double* __restrict__ r_t, double* __restrict__ lamT, double* Wt,
+// bipgo.py:323-332 (+ Wt = Lambda_T Y_t, the time half of the next L-apply).  Yt12 / Wt12 use the
+// padded gather layout (3 rows x 4 doubles) and may alias.
+__global__ void __launch_bounds__(NODE_THREADS) dual_update_kernel(const double* Yt12, double* __restrict__ r_t, double* __restrict__ lamT, double* Wt12,
                                    int64_t n_t) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_t) return;
     double y[9], rot[9], si[9], w[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) y[i] = Yt[9 * t + i];
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) y[3 * i + j] = Yt12[GSTRIDE * t + 4 * i + j];
     svd3_factors(y, rot, nullptr, si);
     mm3(si, y, w);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         r_t[9 * t + i] = rot[i];
         lamT[9 * t + i] = si[i];
-        if (Wt) Wt[9 * t + i] = w[i];
+    }
+    if (Wt12) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Wt12[GSTRIDE * t + 4 * i + j] = w[3 * i + j];
+            Wt12[GSTRIDE * t + 4 * i + 3] = 0.0;
+        }
     }
 }
 
@@ -115,7 +125,7 @@ __global__ void svd_factors_batch_kernel(const double* __restrict__ M, double* r
 inline int64_t align256(int64_t b) { return (b + 255) & ~(int64_t)255; }
 
 struct So3Work {
-    double *X, *AX, *W, *AW, *P, *AP, *Y, *lamC, *lamCinv, *degc, *lamT, *Wt, *small, *partial;
+    double *X, *AX, *W, *AW, *P, *AP, *Y, *lamC, *lamCinv, *degc, *Xpad, *lamT, *Wt, *small, *partial;
     int64_t bytes;
 };
 
@@ -131,7 +141,8 @@ inline So3Work carve_so3(void* base, int64_t n_c, int64_t n_t) {
     w.X = take(9 * n_c); w.AX = take(9 * n_c); w.W = take(9 * n_c); w.AW = take(9 * n_c);
     w.P = take(9 * n_c); w.AP = take(9 * n_c); w.Y = take(9 * n_c);
     w.lamC = take(9 * n_c); w.lamCinv = take(9 * n_c); w.degc = take(n_c);
-    w.lamT = take(9 * n_t); w.Wt = take(9 * n_t);
+    w.Xpad = take(GSTRIDE * n_c);
+    w.lamT = take(9 * n_t); w.Wt = take(GSTRIDE * n_t);
     w.small = take(SM_SIZE);
     w.partial = take(3 * (int64_t)1024 * LOB_NRED);
     w.bytes = off;
@@ -161,19 +172,22 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     int status = VB_STATUS_OK;
 
     auto time_pass = [&](int mode, const double* X, double* out) -> int {
-        S->time_passes++; S->kernel_launches++;
-        return launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, X, w.lamT, out, n_t, st);
+        S->time_passes++; S->kernel_launches += 2;
+        int rc = launch_pad_blocks(X, w.Xpad, n_c, st);   // gather source layout: 3 rows x 4 doubles
+        if (rc) return rc;
+        return launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, w.Xpad, w.lamT, out, n_t, st);
     };
     auto cam_pass = [&](const double* Wt, double* Y) -> int {
         VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
         S->cam_passes++; S->kernel_launches++;
-        int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->tile_end, g->c_time, g->c_B, Wt, Y, g->n_tiles, st);
+        int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, Wt, Y, g->n_tiles, st);
         if (rc) return rc;
         if (opt->allreduce) return opt->allreduce(opt->allreduce_ctx, Y, 9 * n_c, (void*)st);
         return 0;
     };
 #define VB_RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
+    if (n_t > 0) VB_CHECK(cudaMemsetAsync(w.Wt, 0, GSTRIDE * n_t * sizeof(double), st));   // pad lanes of the rows
     // initial duals (global camera degree on edge-sharded runs)
     VB_CHECK(cudaMemcpyAsync(w.degc, g->deg_c, n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (opt->allreduce) VB_RC(opt->allreduce(opt->allreduce_ctx, w.degc, n_c, (void*)st));

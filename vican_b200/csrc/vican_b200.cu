@@ -182,8 +182,11 @@ int vb_pass_time(const vb_graph* g, int mode, const double* X, const double* lam
 }
 
 int vb_pass_cam(const vb_graph* g, const double* W, double* Y, void* stream) {
-    return launch_pass_cam(g->tile_cam, g->tile_start, g->tile_end, g->c_time, g->c_B, W, Y, g->n_tiles,
-                           (cudaStream_t)stream);
+    return launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, W, Y, g->n_tiles, (cudaStream_t)stream);
+}
+
+int vb_pad_blocks(const double* src9, double* dst12, int64_t n, void* stream) {
+    return launch_pad_blocks(src9, dst12, n, (cudaStream_t)stream);
 }
 
 int vb_primal_update(const double* M, double* r_c, double* lamC, double* lamCinv, int64_t n_c, void* stream) {

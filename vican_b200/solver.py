@@ -126,10 +126,10 @@ class DeviceGraph:
     # ---- algorithmic bytes of one edge pass (76 B / edge + node traffic) ----
     def pass_bytes(self, kind: str) -> int:
         E, n_c, n_t = self.n_edges, self.n_c, self.n_t
-        if kind == "time":     # blocks + cam index, row pointers, Lambda_T read, W write, X gather source
-            return 76 * E + 4 * (n_t + 1) + 72 * n_t + 72 * n_t + 72 * n_c
-        if kind == "cam":      # blocks + time index, tile table, W gather source, Y accumulate
-            return 76 * E + 12 * self.n_tiles + 72 * n_t + 2 * 72 * n_c
+        if kind == "time":     # blocks + cam index, row pointers, Lambda_T read, W write (padded), X gather source
+            return 76 * E + 4 * (n_t + 1) + 72 * n_t + 96 * n_t + 96 * n_c
+        if kind == "cam":      # blocks + time index, tile table, W gather source (padded), Y accumulate
+            return 76 * E + 8 * self.n_tiles + 96 * n_t + 2 * 72 * n_c
         raise ValueError(kind)
 
 
