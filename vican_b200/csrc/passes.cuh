@@ -15,7 +15,7 @@
 // Kernel structure (third generation; profiles/r1_edge_pass_history.md has the measurements
 // that led here):
 //  * every warp is an independent pipeline that owns segments warp, warp+W, ... (a time node or
-//    a camera tile).  One elected lane streams the NEXT work item (<= 64 edges: their 72-byte
+//    a camera tile).  One elected lane streams the NEXT work item (<= 50 edges: their 72-byte
 //    blocks and 4-byte indices) into the warp's double-buffered shared-memory stage with two
 //    cp.async.bulk copies (TMA, mbarrier completion, L2 evict-first) while the warp consumes
 //    the current item.  No CTA-wide synchronisation exists.
@@ -42,10 +42,10 @@ constexpr int GSTRIDE = 12;   // doubles per gathered node block: 3 rows x (3 + 
 constexpr int PASS_THREADS = 128;          // 4 independent warp pipelines per CTA
 constexpr int PASS_CTAS_PER_SM = 4;        // 4 x ~42 KB shared memory, <= 127 registers
 constexpr int PASS_WARPS = PASS_THREADS / 32;
-constexpr int ITEM_EDGES = 64;
-constexpr int BUF_B_BYTES = (ITEM_EDGES + 2) * 72;                    // 4752, multiple of 16
-constexpr int BUF_I_BYTES = (ITEM_EDGES + 8) * 4;                     // 288
-constexpr int BUF_BYTES = ((BUF_B_BYTES + BUF_I_BYTES + 127) / 128) * 128;   // 5120
+constexpr int ITEM_EDGES = 50;                                        // one work item = 5 rounds of 10 edges
+constexpr int BUF_B_BYTES = (ITEM_EDGES + 2) * 72;                    // 3744, multiple of 16
+constexpr int BUF_I_BYTES = 240;                                      // >= (ITEM_EDGES + 6) * 4, multiple of 16
+constexpr int BUF_BYTES = ((BUF_B_BYTES + BUF_I_BYTES + 127) / 128) * 128;   // 4096
 constexpr int WARP_SCRATCH = 128;                                     // 9 doubles of epilogue scratch
 constexpr int WARP_SMEM = 2 * BUF_BYTES + WARP_SCRATCH;
 constexpr int PASS_SMEM = PASS_WARPS * WARP_SMEM + PASS_WARPS * 2 * 8;
@@ -231,12 +231,11 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
             const int* sI = reinterpret_cast<const int*>(bufp + BUF_B_BYTES);
             const int offB = ca - (ca & ~1), offI = ca - (ca & ~3);
             const int n_e = cb - ca;
+            // all gathers of the item are issued back to back (one exposed L2 round trip per item)
             constexpr int R = EDGES_PER_ROUND;
-            int g0 = 0;
-            for (; g0 + 4 * R <= n_e; g0 += 4 * R) edge_rounds<TR, 4>(sB, sI, G, offB, offI, g0, n_e, e, k, acc);
-            if (g0 + 2 * R <= n_e) { edge_rounds<TR, 2>(sB, sI, G, offB, offI, g0, n_e, e, k, acc); g0 += 2 * R; }
-            if (g0 + R <= n_e) { edge_rounds<TR, 1>(sB, sI, G, offB, offI, g0, n_e, e, k, acc); g0 += R; }
-            if (g0 < n_e) edge_rounds<TR, 1>(sB, sI, G, offB, offI, g0, n_e, e, k, acc);
+            if (n_e > 3 * R) edge_rounds<TR, 5>(sB, sI, G, offB, offI, 0, n_e, e, k, acc);
+            else if (n_e > R) edge_rounds<TR, 3>(sB, sI, G, offB, offI, 0, n_e, e, k, acc);
+            else edge_rounds<TR, 1>(sB, sI, G, offB, offI, 0, n_e, e, k, acc);
         }
         // ---- segment finished: combine the 30 private sums and emit
         if (cb >= ce) {

@@ -48,10 +48,10 @@ class Comm:
 
 
 def default_tile_len(n_edges: int, n_sms: int = 148) -> int:
-    """Camera-tile length: a multiple of 24 edges (one index chunk), sized so the camera pass
-    has a few thousand warps but at most ~400 edges per 9 fp64 atomics."""
-    tl = (n_edges // (n_sms * 32)) // 24 * 24
-    return int(min(max(tl, 24), 384))
+    """Camera-tile length: a multiple of 50 edges (one work item of the edge pass), sized so the
+    camera pass has a few thousand warps but at most 400 edges per 9 fp64 atomics."""
+    tl = (n_edges // (n_sms * 32)) // 50 * 50
+    return int(min(max(tl, 50), 400))
 
 
 class DeviceGraph:
