@@ -149,8 +149,8 @@ __device__ __forceinline__ double reduce_scatter9(const double (&v)[9], int lane
 // MODE 0: out_t = Lambda_T[t] * sum B^T X   (padded rows)   -- L-apply / primal multiply (bipgo.py:300)
 // MODE 1: out_t = sum B^T X                 (padded rows)   -- dual gather Y = P^T r_c (bipgo.py:318)
 // MODE 2: Y_c  += sum over tile of B W      (compact 9, fp64 atomics per TILE, not per edge)
-template <int MODE>
-__global__ void __launch_bounds__(PASS_THREADS, PASS_CTAS_PER_SM)
+template <int MODE, int CTAS>
+__global__ void __launch_bounds__(PASS_THREADS, CTAS)
 edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ idx,
                  const double* __restrict__ B, const double* __restrict__ G, const double* __restrict__ lamT,
                  double* __restrict__ out, int n_seg) {
@@ -289,23 +289,43 @@ inline int launch_pad_blocks(const double* src, double* dst, int64_t n, cudaStre
     return 0;
 }
 
-inline int pass_grid(int64_t n_segments) {
+inline int pass_grid(int64_t n_segments, int ctas_per_sm) {
     const int64_t want = (n_segments + PASS_WARPS - 1) / PASS_WARPS;
-    const int64_t cap = (int64_t)sm_count() * PASS_CTAS_PER_SM;   // persistent: exactly one resident wave
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;   // persistent: exactly one resident wave
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+inline int pass_ctas() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("VB_PASS_CTAS");
+        v = e ? atoi(e) : PASS_CTAS_PER_SM;
+        if (v < 4 || v > 6) v = PASS_CTAS_PER_SM;
+    }
+    return v;
+}
+
+template <int MODE, int CTAS>
+inline int launch_edge_pass_c(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
+                              const double* lamT, double* out, int64_t n_seg, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VB_CHECK(cudaFuncSetAttribute(edge_pass_kernel<MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
+        attr_set = true;
+    }
+    edge_pass_kernel<MODE, CTAS><<<pass_grid(n_seg, CTAS), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg);
+    VB_KERNEL_CHECK();
+    return 0;
 }
 
 template <int MODE>
 inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
                             const double* lamT, double* out, int64_t n_seg, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        VB_CHECK(cudaFuncSetAttribute(edge_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
-        attr_set = true;
+    switch (pass_ctas()) {
+        case 5: return launch_edge_pass_c<MODE, 5>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st);
+        case 6: return launch_edge_pass_c<MODE, 6>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st);
+        default: return launch_edge_pass_c<MODE, 4>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st);
     }
-    edge_pass_kernel<MODE><<<pass_grid(n_seg), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg);
-    VB_KERNEL_CHECK();
-    return 0;
 }
 
 // NOTE: idx must be readable up to index ((E+3)&~3)-1 and B up to edge ((E+1)&~1)-1 (the bulk
