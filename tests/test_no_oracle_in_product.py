@@ -1,0 +1,26 @@
+"""The oracle is test infrastructure: nothing under vican_b200/ (the product) nor bench.py's GPU arm
+may import it, and the product must not carry a CPU fallback."""
+import os
+import re
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vican_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+                # comments may cite scipy (the algorithm being replaced); no product file may import it
+                assert not re.search(r"^\s*(from|import)\s+scipy\b", src, flags=re.M), "scipy imported in " + f
+
+
+def test_bench_uses_oracle_only_for_cpu_legs():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle import", src)]
+    assert len(uses) == 1
+    # the single import lives in cpu_sample_solve (cpu_baseline / --impl reference legs)
+    fn_start = src.rfind("def ", 0, uses[0])
+    assert src[fn_start:].startswith("def cpu_sample_solve")
