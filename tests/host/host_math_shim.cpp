@@ -10,6 +10,9 @@ void h_svd3(const double* M, double* U, double* S, double* V, int64_t n) {
 void h_svd3_factors(const double* M, double* rot, double* spos, double* sinv, int64_t n) {
     for (int64_t i = 0; i < n; ++i) vb::svd3_factors(M + 9 * i, rot + 9 * i, spos + 9 * i, sinv + 9 * i);
 }
+void h_node_factors(const double* M, double* rot, double* spos, double* sinv, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) vb::node_factors(M + 9 * i, rot + 9 * i, spos + 9 * i, sinv + 9 * i);
+}
 void h_inv3(const double* A, double* I, int64_t n) {
     for (int64_t i = 0; i < n; ++i) vb::inv3(A + 9 * i, I + 9 * i);
 }

@@ -56,6 +56,29 @@ def test_svd3_factors_random(lib):
     assert np.allclose(np.linalg.det(rot), 1.0, atol=1e-12)
 
 
+def test_node_factors_newton_polar_matches_svd(lib):
+    """node_factors = scaled-Newton polar route with SVD fallback: same three factors as LAPACK."""
+    rng = np.random.default_rng(3)
+    n = 30000
+    from vican_b200.synthetic import random_rotations, so3_exp
+    M = rng.standard_normal((n, 3, 3)) * rng.uniform(1e-2, 1e2, (n, 1, 1))
+    R = random_rotations(rng, n // 2)
+    M[: n // 2] = sum(R @ so3_exp(rng.normal(0, 0.05, (n // 2, 3))) * rng.uniform(0.5, 1.5, (n // 2, 1, 1)) for _ in range(20))
+    M[n // 2: n // 2 + 200, :, 0] *= -1                      # det < 0 -> SVD fallback (det fix)
+    M[n // 2 + 200: n // 2 + 300, :, 2] = M[n // 2 + 200: n // 2 + 300, :, 0] * (1 + 1e-11)   # near singular
+    rot = np.zeros_like(M); sp = np.zeros_like(M); si = np.zeros_like(M)
+    lib.h_node_factors(P(M), P(rot), P(sp), P(si), ctypes.c_int64(n))
+    r0, p0, i0, S = ref_factors(M)
+    cond = S[:, 0] / S[:, 2]
+    good = cond < 1e8
+    assert np.all(np.abs(rot - r0).max(axis=(1, 2))[good] < 1e-13 * cond[good])
+    assert np.all(np.abs(sp - p0).max(axis=(1, 2))[good] < 1e-13 * (S[:, 0] * cond)[good])
+    assert np.all(np.abs(si - i0).max(axis=(1, 2))[good] < 1e-13 * (cond * cond / S[:, 2])[good])
+    assert np.allclose(np.linalg.det(rot[good]), 1.0, atol=1e-12)
+    # consistent rotations (what the solver feeds): essentially exact
+    assert np.abs(rot[: n // 2] - r0[: n // 2]).max() < 1e-13
+
+
 def test_svd3_singular_values_and_orthogonality(lib):
     rng = np.random.default_rng(1)
     n = 5000

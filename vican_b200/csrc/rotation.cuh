@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(NODE_THREADS) gauge_project_kernel(const doubl
     for (int i = 0; i < 9; ++i) { v0[i] = V[i]; v[i] = V[9 * c + i]; }
     inv3(v0, v0i);
     mm3(v, v0i, x);
-    svd3_factors(x, rot, nullptr, nullptr);
+    node_factors(x, rot, nullptr, nullptr);
 #pragma unroll
     for (int i = 0; i < 9; ++i) r_c[9 * c + i] = rot[i];
 }
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const doubl
     double m[9], rot[9], sp[9], si[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) m[i] = M[9 * c + i];
-    svd3_factors(m, rot, sp, si);
+    node_factors(m, rot, sp, si);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         r_c[9 * c + i] = rot[i];
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(NODE_THREADS) dual_update_kernel(const double*
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) y[3 * i + j] = Yt12[GSTRIDE * t + 4 * i + j];
-    svd3_factors(y, rot, nullptr, si);
+    node_factors(y, rot, nullptr, si);
     mm3(si, y, w);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -101,7 +101,7 @@ __global__ void polar_batch_kernel(const double* __restrict__ M, double* __restr
     double m[9], rot[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = M[9 * i + k];
-    svd3_factors(m, rot, nullptr, nullptr);
+    node_factors(m, rot, nullptr, nullptr);
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[9 * i + k] = rot[k];
 }
@@ -112,7 +112,7 @@ __global__ void svd_factors_batch_kernel(const double* __restrict__ M, double* r
     double m[9], a[9], b[9], c[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = M[9 * i + k];
-    svd3_factors(m, a, b, c);
+    node_factors(m, a, b, c);
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         if (rot) rot[9 * i + k] = a[k];

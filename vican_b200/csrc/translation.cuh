@@ -12,6 +12,7 @@
 
 #include "../../include/vican_b200.h"
 #include "common.cuh"
+#include "passes.cuh"
 #include "rotation.cuh"
 
 namespace vb {
@@ -88,8 +89,9 @@ inline CgWork carve_cg(void* base, int64_t n_c, int64_t n_t) {
         off += align256(nd * (int64_t)sizeof(double));
         return r;
     };
-    w.r_c = take(3 * n_c); w.p_c = take(3 * n_c); w.q_c = take(3 * n_c + 8); w.dg_c = take(n_c);
-    w.r_t = take(3 * n_t); w.p_t = take(3 * n_t); w.q_t = take(3 * n_t); w.dg_t = take(n_t);
+    // search directions are kept PADDED ([n][4], 32-byte rows) so the matvec gathers them with one 256-bit load
+    w.r_c = take(3 * n_c); w.p_c = take(4 * n_c); w.q_c = take(3 * n_c + 8); w.dg_c = take(n_c);
+    w.r_t = take(3 * n_t); w.p_t = take(4 * n_t); w.q_t = take(3 * n_t); w.dg_t = take(n_t);
     w.sc = take(CG_NSCAL);
     w.bytes = off;
     return w;
@@ -135,9 +137,10 @@ __global__ void cg_init_kernel(const double* __restrict__ b, const double* __res
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const double bv = b[3 * i + k];
-            x[3 * i + k] = 0.0; r[3 * i + k] = bv; p[3 * i + k] = 0.0;
+            x[3 * i + k] = 0.0; r[3 * i + k] = bv; p[4 * i + k] = 0.0;
             v[0] += bv * bv * d; v[1] += bv * bv;
         }
+        p[4 * i + 3] = 0.0;
     }
     double* const dst[2] = {sc + rho_slot, sc + rn_slot};
     block_atomic_sum<2>(v, dst);
@@ -170,7 +173,7 @@ __global__ void cg_dir_kernel(const double* __restrict__ r, const double* __rest
     const double beta = sc[CG_BETA];
     const double d = jacobi ? 1.0 / dg[i] : 1.0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) p[3 * i + k] = r[3 * i + k] * d + beta * p[3 * i + k];
+    for (int k = 0; k < 3; ++k) p[4 * i + k] = r[3 * i + k] * d + beta * p[4 * i + k];
 }
 
 // time side of q = (J^T J) p : warp per time node; also accumulates p_t . q_t
@@ -182,12 +185,14 @@ __global__ void cg_time_kernel(const int* __restrict__ rowptr, const int* __rest
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double dot[1] = {0.0};
     if (warp < n_t) {
-        const double x0 = p_t[3 * warp], x1 = p_t[3 * warp + 1], x2 = p_t[3 * warp + 2];
+        const double x0 = p_t[4 * warp], x1 = p_t[4 * warp + 1], x2 = p_t[4 * warp + 2];
         double a0 = 0, a1 = 0, a2 = 0;
         for (int i = rowptr[warp] + lane; i < rowptr[warp + 1]; i += 32) {
             const int64_t c = cam[i];
             const double ww = w[i];
-            a0 += ww * (x0 - p_c[3 * c]); a1 += ww * (x1 - p_c[3 * c + 1]); a2 += ww * (x2 - p_c[3 * c + 2]);
+            double g0, g1, g2;
+            ld_row256(p_c + 4 * c, g0, g1, g2);
+            a0 += ww * (x0 - g0); a1 += ww * (x1 - g1); a2 += ww * (x2 - g2);
         }
         a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
         if (lane == 0) {
@@ -208,23 +213,25 @@ __global__ void cg_cam_kernel(const int* __restrict__ tile_cam, const int* __res
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= n_tiles) return;
     const int64_t c = tile_cam[warp];
-    const double x0 = p_c[3 * c], x1 = p_c[3 * c + 1], x2 = p_c[3 * c + 2];
+    const double x0 = p_c[4 * c], x1 = p_c[4 * c + 1], x2 = p_c[4 * c + 2];
     double a0 = 0, a1 = 0, a2 = 0;
     for (int i = tile_start[warp] + lane; i < tile_end[warp]; i += 32) {
         const int64_t t = tidx[i];
         const double ww = w[i];
-        a0 += ww * (x0 - p_t[3 * t]); a1 += ww * (x1 - p_t[3 * t + 1]); a2 += ww * (x2 - p_t[3 * t + 2]);
+        double g0, g1, g2;
+        ld_row256(p_t + 4 * t, g0, g1, g2);
+        a0 += ww * (x0 - g0); a1 += ww * (x1 - g1); a2 += ww * (x2 - g2);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { atomicAdd(q_c + 3 * c, a0); atomicAdd(q_c + 3 * c + 1, a1); atomicAdd(q_c + 3 * c + 2, a2); }
 }
 
 // p_c . q_c (after the camera pass / all-reduce); the time part may have been packed at q_c[3 n_c]
-__global__ void cg_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* sc, int slot) {
+__global__ void cg_dot_kernel(const double* __restrict__ p4, const double* __restrict__ q3, int64_t n_nodes, double* sc, int slot) {
     if (sc[CG_DONE] != 0.0) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double v[1] = {0.0};
-    if (i < n) v[0] = a[i] * b[i];
+    if (i < n_nodes) v[0] = p4[4 * i] * q3[3 * i] + p4[4 * i + 1] * q3[3 * i + 1] + p4[4 * i + 2] * q3[3 * i + 2];
     double* const dst[1] = {sc + slot};
     block_atomic_sum<1>(v, dst);
 }
@@ -247,7 +254,7 @@ __global__ void cg_update_kernel(const double* __restrict__ p, const double* __r
         const double d = jacobi ? 1.0 / dg[i] : 1.0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            x[3 * i + k] += alpha * p[3 * i + k];
+            x[3 * i + k] += alpha * p[4 * i + k];
             const double rv = r[3 * i + k] - alpha * q[3 * i + k];
             r[3 * i + k] = rv;
             v[0] += rv * rv * d; v[1] += rv * rv;
@@ -316,7 +323,7 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
             if (rc) return rc;
             unpack_scalars_kernel<<<1, 1, 0, st>>>(pack, w.sc, CG_PQ_T, -1, -1);
         }
-        cg_dot_kernel<<<tr_grid(3 * n_c), TR_THREADS, 0, st>>>(w.p_c, w.q_c, 3 * n_c, w.sc, CG_PQ_C);
+        cg_dot_kernel<<<tr_grid(n_c), TR_THREADS, 0, st>>>(w.p_c, w.q_c, n_c, w.sc, CG_PQ_C);
         cg_scalar_alpha_kernel<<<1, 1, 0, st>>>(w.sc);
         cg_update_kernel<<<tr_grid(n_c), TR_THREADS, 0, st>>>(w.p_c, w.q_c, w.dg_c, jacobi, x_c, w.r_c, n_c, w.sc, CG_RHO_NEXT_C, CG_RN2_C);
         if (n_t > 0) cg_update_kernel<<<tr_grid(n_t), TR_THREADS, 0, st>>>(w.p_t, w.q_t, w.dg_t, jacobi, x_t, w.r_t, n_t, w.sc, CG_RHO_NEXT_T, CG_RN2_T);
