@@ -36,12 +36,13 @@ typedef struct vb_graph {
     int64_t n_t;            /* time nodes (local to this rank) */
     int64_t n_edges;        /* aggregated edges E (local) */
     int64_t n_tiles;        /* camera tiles */
+    int64_t n_windows;      /* time windows of the camera-pass order */
     const int32_t* t_rowptr;   /* [n_t+1] */
     const int32_t* t_cam;      /* [E]   camera of each time-sorted edge */
     const double*  t_B;        /* [E][9] block  sum k_r R_cm R_m^T R_0 */
     const double*  t_w;        /* [E]   sum k_t^2   (translation Laplacian weight) */
-    const int32_t* c_colptr;   /* [n_c+1] camera-major segments (through c_perm) */
-    const int32_t* c_perm;     /* [E]   camera-major position -> time-sorted edge */
+    const int32_t* c_segptr;   /* [n_windows*n_c+1] runs of the camera-pass order: run (w, c) = [c_segptr[w*n_c+c], +1) */
+    const int32_t* c_order;    /* [E]   camera-pass position -> time-sorted edge */
     const int32_t* c_time;     /* [E]   time node of each camera-pass edge ((window, camera, time) order) */
     const double*  c_B;        /* [E][9] */
     const double*  c_w;        /* [E] */
@@ -107,23 +108,24 @@ int64_t vb_ingest_workspace_bytes(int64_t n_raw);
 int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64_t n_c, int64_t n_t,
                    int32_t* raw_perm, int32_t* raw_pair, int64_t* h_n_pairs, void* workspace,
                    int64_t workspace_bytes, void* stream);
-/* step 2: fold + aggregate into the time-sorted arrays, build the camera-pass copy, row /
- * column pointers, degrees and camera tiles.  pair_start [E+1] (into the sorted raw list) and
- * c_perm [E] (camera-major position -> time-sorted edge, with c_colptr) serve the per-camera
- * reductions of the translation stage.  The camera-pass arrays c_B / c_time / c_w are ordered
- * by (time window, camera, time) -- c_order [E] maps their positions to time-sorted edges --
- * and cut into tiles (runs of one camera, <= tile_len edges, contiguous: tile_start carries a
+/* step 2: fold + aggregate into the time-sorted arrays, build the camera-pass copy, row
+ * pointers, degrees and camera tiles.  pair_start [E+1] indexes the sorted raw list.  The
+ * camera-pass arrays c_B / c_time / c_w are ordered by (time window, camera, time): c_order [E]
+ * maps their positions to time-sorted edges, c_segptr [n_windows*n_c+1] delimits the run of every
+ * (window, camera) -- per-camera reductions walk a camera's n_windows runs -- and the runs are cut
+ * into tiles (runs of one camera, <= tile_len edges, contiguous: tile_start carries a
  * sentinel tile_start[n_tiles] = E).  tile arrays must hold vb_ingest_max_tiles + 1 entries.
  * PADDING: t_B / c_B must be allocated for E + 2 blocks and t_cam / c_time for E + 8 indices
  * (the edge passes stream them with 16-byte granular bulk copies). */
 int64_t vb_ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len);
+int64_t vb_ingest_windows(int64_t n_edges, int64_t n_c, int64_t tile_len);
 int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* marker, const double* R,
                     const double* k_r, const double* k_t, const double* markerC, int64_t n_raw,
                     int round_kr_f32, const int32_t* raw_perm, const int32_t* raw_pair, int64_t n_pairs,
                     int64_t n_c, int64_t n_t, int64_t tile_len,
                     int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
-                    int32_t* pair_start, int32_t* c_colptr, int32_t* c_time, double* c_B, double* c_w,
-                    int32_t* c_perm, int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_end,
+                    int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
+                    int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_end,
                     int64_t* h_n_tiles, double* deg_t, double* deg_c, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
@@ -158,7 +160,7 @@ int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, do
  * when non-NULL (needed by LSQR).  rhs = J^T t~ : rhs_c [n_c][3] (caller zeroes), rhs_t [n_t][3]. */
 int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
                  const double* t_cm, const double* k_t, const double* marker_q, const double* r_c,
-                 const double* r_t, const int32_t* t_time, const int32_t* c_perm, double* pair_g,
+                 const double* r_t, const int32_t* t_time, double* pair_g,
                  double* d_sorted, double* rhs_c, double* rhs_t, void* stream);
 int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t);
 /* Conjugate gradients on J^T J x = J^T t~ replaying scipy.sparse.linalg.cg as the reference

@@ -30,9 +30,9 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, VP, VP, I64, VP)
 
 class VbGraph(C.Structure):
     _fields_ = [
-        ("n_c", I64), ("n_t", I64), ("n_edges", I64), ("n_tiles", I64),
+        ("n_c", I64), ("n_t", I64), ("n_edges", I64), ("n_tiles", I64), ("n_windows", I64),
         ("t_rowptr", VP), ("t_cam", VP), ("t_B", VP), ("t_w", VP),
-        ("c_colptr", VP), ("c_perm", VP), ("c_time", VP), ("c_B", VP), ("c_w", VP),
+        ("c_segptr", VP), ("c_order", VP), ("c_time", VP), ("c_B", VP), ("c_w", VP),
         ("tile_cam", VP), ("tile_start", VP), ("tile_end", VP),
         ("deg_t", VP), ("deg_c", VP),
     ]
@@ -61,8 +61,9 @@ SIGNATURES = {
     "vb_ingest_workspace_bytes": (I64, [I64]),
     "vb_ingest_sort": (C.c_int, [VP, VP, I64, I64, I64, VP, VP, c_i64p, VP, I64, VP]),
     "vb_ingest_max_tiles": (I64, [I64, I64, I64]),
+    "vb_ingest_windows": (I64, [I64, I64, I64]),
     "vb_ingest_build": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, I64, C.c_int, VP, VP, I64, I64, I64, I64,
-                                  VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, c_i64p, VP, VP,
+                                  VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, c_i64p, VP, VP,
                                   VP, I64, VP]),
     "vb_pad_blocks": (C.c_int, [VP, VP, I64, VP]),
     "vb_pass_time": (C.c_int, [C.POINTER(VbGraph), C.c_int, VP, VP, VP, VP]),
@@ -73,7 +74,7 @@ SIGNATURES = {
     "vb_so3sync_workspace_bytes": (I64, [I64, I64]),
     "vb_so3sync_run": (C.c_int, [C.POINTER(VbGraph), C.POINTER(VbSo3Options), VP, VP, VP, I64,
                                  C.POINTER(VbSo3Stats), VP]),
-    "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+    "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "vb_trans_cg_workspace_bytes": (I64, [I64, I64]),
     "vb_trans_cg": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, F64, I64, C.c_int, c_i32p, VP, I64, VP, VP, VP]),
     "vb_trans_lsqr_workspace_bytes": (I64, [I64, I64, I64]),

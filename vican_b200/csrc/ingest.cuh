@@ -165,6 +165,23 @@ __global__ void window_seg_kernel(const uint64_t* __restrict__ keys_sorted, int6
     seg[i] = (int)(keys_sorted[i] / (uint64_t)n_t);
 }
 
+// warp per camera: out[c] = sum over the camera's (window, camera) runs of a[order[i]] -- the
+// camera-pass order keeps every camera's edges in n_win contiguous runs, so per-camera reductions
+// need no camera-major copy (fixed summation order: deterministic)
+__global__ void cam_runs_sum_kernel(const int* __restrict__ segptr, int64_t n_win, int64_t n_c, const int* __restrict__ order,
+                                    const double* __restrict__ a, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_c) return;
+    double acc = 0.0;
+    for (int64_t wdw = 0; wdw < n_win; ++wdw) {
+        const int s = segptr[wdw * n_c + c], e = segptr[wdw * n_c + c + 1];
+        for (int i = s + lane; i < e; i += 32) acc += a[order ? order[i] : i];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[c] = acc;
+}
+
 struct IngestWork {
     uint64_t *keys_a, *keys_b;
     int *vals_a, *tmp_a, *tmp_b, *tmp_c, *tmp_d;

@@ -12,6 +12,7 @@
 
 #include "../../include/vican_b200.h"
 #include "common.cuh"
+#include "ingest.cuh"
 #include "passes.cuh"
 #include "rotation.cuh"
 
@@ -66,6 +67,24 @@ __global__ void seg_sum3_kernel(const int* __restrict__ ptr, const int* __restri
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { out[3 * warp] += sign * a0; out[3 * warp + 1] += sign * a1; out[3 * warp + 2] += sign * a2; }
+}
+
+// warp per camera: out[c] += sign * sum over the camera's (window, camera) runs of g[order[i]]
+__global__ void cam_runs_sum3_kernel(const int* __restrict__ segptr, int64_t n_win, int64_t n_c, const int* __restrict__ order,
+                                     const double* __restrict__ g, double sign, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_c) return;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int64_t wdw = 0; wdw < n_win; ++wdw) {
+        const int s = segptr[wdw * n_c + c], e = segptr[wdw * n_c + c + 1];
+        for (int i = s + lane; i < e; i += 32) {
+            const int64_t j = order[i];
+            a0 += g[3 * j]; a1 += g[3 * j + 1]; a2 += g[3 * j + 2];
+        }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { out[3 * c] += sign * a0; out[3 * c + 1] += sign * a1; out[3 * c + 2] += sign * a2; }
 }
 
 // ------------------------------------------------------------------------------------- CG
@@ -176,29 +195,44 @@ __global__ void cg_dir_kernel(const double* __restrict__ r, const double* __rest
     for (int k = 0; k < 3; ++k) p[4 * i + k] = r[3 * i + k] * d + beta * p[4 * i + k];
 }
 
-// time side of q = (J^T J) p : warp per time node; also accumulates p_t . q_t
-__global__ void cg_time_kernel(const int* __restrict__ rowptr, const int* __restrict__ cam, const double* __restrict__ w,
-                               const double* __restrict__ p_c, const double* __restrict__ p_t, double* __restrict__ q_t,
-                               int64_t n_t, double* sc) {
+// time side of q = (J^T J) p : warp per time node (persistent, grid-stride); also accumulates p_t . q_t.
+// Two edges per lane are loaded back to back (degree <= 64 needs a single round trip) and the row
+// pointers of the warp's next node are fetched while the current one is reduced.
+__global__ void __launch_bounds__(TR_THREADS)
+cg_time_kernel(const int* __restrict__ rowptr, const int* __restrict__ cam, const double* __restrict__ w,
+               const double* __restrict__ p_c, const double* __restrict__ p_t, double* __restrict__ q_t,
+               int64_t n_t, double* sc) {
     if (sc[CG_DONE] != 0.0) return;
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double dot[1] = {0.0};
-    if (warp < n_t) {
-        const double x0 = p_t[4 * warp], x1 = p_t[4 * warp + 1], x2 = p_t[4 * warp + 2];
+    int s = 0, e = 0;
+    if (warp0 < n_t) { s = __ldg(rowptr + warp0); e = __ldg(rowptr + warp0 + 1); }
+    for (int64_t node = warp0; node < n_t; node += nwarps) {
+        const int64_t nxt = node + nwarps;
+        int s2 = 0, e2 = 0;
+        if (nxt < n_t) { s2 = __ldg(rowptr + nxt); e2 = __ldg(rowptr + nxt + 1); }
+        const double x0 = p_t[4 * node], x1 = p_t[4 * node + 1], x2 = p_t[4 * node + 2];
         double a0 = 0, a1 = 0, a2 = 0;
-        for (int i = rowptr[warp] + lane; i < rowptr[warp + 1]; i += 32) {
-            const int64_t c = cam[i];
-            const double ww = w[i];
-            double g0, g1, g2;
-            ld_row256(p_c + 4 * c, g0, g1, g2);
-            a0 += ww * (x0 - g0); a1 += ww * (x1 - g1); a2 += ww * (x2 - g2);
+        for (int i = s + lane; i < e; i += 64) {
+            const int i2 = i + 32;
+            const bool two = i2 < e;
+            const int64_t ca = cam[i], cb = two ? cam[i2] : 0;
+            const double wa = w[i], wb = two ? w[i2] : 0.0;
+            double g0, g1, g2, h0 = x0, h1 = x1, h2 = x2;
+            ld_row256(p_c + 4 * ca, g0, g1, g2);
+            if (two) ld_row256(p_c + 4 * cb, h0, h1, h2);
+            a0 += wa * (x0 - g0) + wb * (x0 - h0);
+            a1 += wa * (x1 - g1) + wb * (x1 - h1);
+            a2 += wa * (x2 - g2) + wb * (x2 - h2);
         }
         a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
         if (lane == 0) {
-            q_t[3 * warp] = a0; q_t[3 * warp + 1] = a1; q_t[3 * warp + 2] = a2;
-            dot[0] = x0 * a0 + x1 * a1 + x2 * a2;
+            q_t[3 * node] = a0; q_t[3 * node + 1] = a1; q_t[3 * node + 2] = a2;
+            dot[0] += x0 * a0 + x1 * a1 + x2 * a2;
         }
+        s = s2; e = e2;
     }
     double* const dst[1] = {sc + CG_PQ_T};
     block_atomic_sum<1>(dot, dst);
@@ -215,12 +249,18 @@ __global__ void cg_cam_kernel(const int* __restrict__ tile_cam, const int* __res
     const int64_t c = tile_cam[warp];
     const double x0 = p_c[4 * c], x1 = p_c[4 * c + 1], x2 = p_c[4 * c + 2];
     double a0 = 0, a1 = 0, a2 = 0;
-    for (int i = tile_start[warp] + lane; i < tile_end[warp]; i += 32) {
-        const int64_t t = tidx[i];
-        const double ww = w[i];
-        double g0, g1, g2;
-        ld_row256(p_t + 4 * t, g0, g1, g2);
-        a0 += ww * (x0 - g0); a1 += ww * (x1 - g1); a2 += ww * (x2 - g2);
+    const int te = tile_end[warp];
+    for (int i = tile_start[warp] + lane; i < te; i += 64) {
+        const int i2 = i + 32;
+        const bool two = i2 < te;
+        const int64_t ta = tidx[i], tb = two ? tidx[i2] : 0;
+        const double wa = w[i], wb = two ? w[i2] : 0.0;
+        double g0, g1, g2, h0 = x0, h1 = x1, h2 = x2;
+        ld_row256(p_t + 4 * ta, g0, g1, g2);
+        if (two) ld_row256(p_t + 4 * tb, h0, h1, h2);
+        a0 += wa * (x0 - g0) + wb * (x0 - h0);
+        a1 += wa * (x1 - g1) + wb * (x1 - h1);
+        a2 += wa * (x2 - g2) + wb * (x2 - h2);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { atomicAdd(q_c + 3 * c, a0); atomicAdd(q_c + 3 * c + 1, a1); atomicAdd(q_c + 3 * c + 2, a2); }
@@ -283,7 +323,7 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     VB_CHECK(cudaMemsetAsync(w.sc, 0, CG_NSCAL * sizeof(double), st));
     if (jacobi) {
         if (n_t > 0) seg_sum1_kernel<<<tr_warp_grid(n_t), TR_THREADS, 0, st>>>(g->t_rowptr, nullptr, g->t_w, w.dg_t, n_t);
-        seg_sum1_kernel<<<tr_warp_grid(n_c), TR_THREADS, 0, st>>>(g->c_colptr, g->c_perm, g->t_w, w.dg_c, n_c);
+        cam_runs_sum_kernel<<<tr_warp_grid(n_c), TR_THREADS, 0, st>>>(g->c_segptr, g->n_windows, n_c, nullptr, g->c_w, w.dg_c);
         if (allreduce) { int rc = allreduce(actx, w.dg_c, n_c, (void*)st); if (rc) return rc; }
     }
     // camera part is replicated across ranks -> counted once on every rank; time part is local
@@ -313,7 +353,12 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
         cg_dir_kernel<<<tr_grid(n_c), TR_THREADS, 0, st>>>(w.r_c, w.dg_c, jacobi, w.p_c, n_c, w.sc);
         if (n_t > 0) cg_dir_kernel<<<tr_grid(n_t), TR_THREADS, 0, st>>>(w.r_t, w.dg_t, jacobi, w.p_t, n_t, w.sc);
         VB_CHECK(cudaMemsetAsync(w.q_c, 0, (3 * n_c + 8) * sizeof(double), st));
-        if (n_t > 0) cg_time_kernel<<<tr_warp_grid(n_t), TR_THREADS, 0, st>>>(g->t_rowptr, g->t_cam, g->t_w, w.p_c, w.p_t, w.q_t, n_t, w.sc);
+        if (n_t > 0) {
+            int tg = tr_warp_grid(n_t);
+            const int cap = sm_count() * 8;   // persistent: 8 CTAs of 256 threads per SM
+            if (tg > cap) tg = cap;
+            cg_time_kernel<<<tg, TR_THREADS, 0, st>>>(g->t_rowptr, g->t_cam, g->t_w, w.p_c, w.p_t, w.q_t, n_t, w.sc);
+        }
         if (g->n_tiles > 0) cg_cam_kernel<<<tr_warp_grid(g->n_tiles), TR_THREADS, 0, st>>>(g->tile_cam, g->tile_start, g->tile_end, g->c_time, g->c_w, w.p_c, w.p_t, w.q_c, g->n_tiles, w.sc);
         VB_KERNEL_CHECK();
         if (allreduce) {

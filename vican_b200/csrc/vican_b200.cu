@@ -122,11 +122,13 @@ int64_t vb_ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len) {
     return ingest_max_tiles(n_edges, n_c, tile_len);
 }
 
+int64_t vb_ingest_windows(int64_t n_edges, int64_t n_c, int64_t tile_len) { return ingest_windows(n_edges, n_c, tile_len); }
+
 int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* marker, const double* R, const double* k_r,
                     const double* k_t, const double* markerC, int64_t n_raw, int round_kr_f32, const int32_t* raw_perm,
                     const int32_t* raw_pair, int64_t n_pairs, int64_t n_c, int64_t n_t, int64_t tile_len,
                     int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
-                    int32_t* pair_start, int32_t* c_colptr, int32_t* c_time, double* c_B, double* c_w, int32_t* c_perm,
+                    int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
                     int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_end, int64_t* h_n_tiles, double* deg_t,
                     double* deg_c, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -140,29 +142,22 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_time, nullptr, t_rowptr, E, n_t);
     seg_sum_kernel<<<ing_grid(n_t * 32), ING_THREADS, 0, st>>>(t_rowptr, nullptr, t_a, deg_t, n_t);
     VB_KERNEL_CHECK();
-    // camera-major permutation + column pointers (small per-camera reductions: degrees, rhs)
-    make_keys_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, t_time, n_t, w.keys_a, w.vals_a, E);
-    size_t tb = w.cub_bytes;
-    VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
-                                             c_perm, (int)E, 0, key_bits(n_c, n_t), st));
-    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, c_perm, c_colptr, E, n_c);
-    seg_sum_kernel<<<ing_grid(n_c * 32), ING_THREADS, 0, st>>>(c_colptr, c_perm, t_a, deg_c, n_c);
-    VB_KERNEL_CHECK();
     // camera-pass copy of the blocks: (time window, camera, time) order, tiles = runs of (window, camera)
     const int64_t n_win = ingest_windows(E, n_c, tile_len);
     const int64_t n_seg = n_win * n_c;
     if (n_seg + 1 > n_raw + 1) return VB_STATUS_BAD_ARGUMENT;
     make_window_keys_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, t_time, n_c, n_t, n_win, w.keys_a, w.vals_a, E);
-    tb = w.cub_bytes;
+    size_t tb = w.cub_bytes;
     VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
                                              c_order, (int)E, 0, key_bits(n_c * n_win, n_t), st));
     window_seg_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.keys_b, n_t, w.tmp_a, E);
-    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.tmp_a, nullptr, w.tmp_b, E, n_seg);
+    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.tmp_a, nullptr, c_segptr, E, n_seg);
+    cam_runs_sum_kernel<<<ing_grid(n_c * 32), ING_THREADS, 0, st>>>(c_segptr, n_win, n_c, c_order, t_a, deg_c);
     gather_cam_sorted_kernel<<<ing_grid(9 * E), ING_THREADS, 0, st>>>(c_order, t_time, t_B, t_w, c_time, c_B, c_w, E);
-    tile_count_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(w.tmp_b, w.tmp_c, n_seg, (int)tile_len);
+    tile_count_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(c_segptr, w.tmp_c, n_seg, (int)tile_len);
     tb = w.cub_bytes;
     VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.tmp_c, w.tmp_d, (int)n_seg, st));
-    tile_fill_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(w.tmp_b, w.tmp_d, tile_cam, tile_start, tile_end, n_seg, n_c, (int)tile_len);
+    tile_fill_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(c_segptr, w.tmp_d, tile_cam, tile_start, tile_end, n_seg, n_c, (int)tile_len);
     VB_KERNEL_CHECK();
     int last_off = 0, last_cnt = 0;
     VB_CHECK(cudaMemcpyAsync(&last_off, w.tmp_d + (n_seg - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -220,8 +215,7 @@ int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, do
 // ---------------------------------------------------------------------------- translation
 int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
                  const double* t_cm, const double* k_t, const double* marker_q, const double* r_c, const double* r_t,
-                 const int32_t* t_time, const int32_t* c_perm, double* pair_g, double* d_sorted, double* rhs_c,
-                 double* rhs_t, void* stream) {
+                 const int32_t* t_time, double* pair_g, double* d_sorted, double* rhs_c, double* rhs_t, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t E = g->n_edges;
     if (E <= 0) return VB_STATUS_BAD_ARGUMENT;
@@ -230,7 +224,7 @@ int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair
     VB_CHECK(cudaMemsetAsync(rhs_c, 0, 3 * g->n_c * sizeof(double), st));
     VB_CHECK(cudaMemsetAsync(rhs_t, 0, 3 * g->n_t * sizeof(double), st));
     seg_sum3_kernel<<<tr_warp_grid(g->n_t), TR_THREADS, 0, st>>>(g->t_rowptr, nullptr, pair_g, 1.0, rhs_t, g->n_t);
-    seg_sum3_kernel<<<tr_warp_grid(g->n_c), TR_THREADS, 0, st>>>(g->c_colptr, c_perm, pair_g, -1.0, rhs_c, g->n_c);
+    cam_runs_sum3_kernel<<<tr_warp_grid(g->n_c), TR_THREADS, 0, st>>>(g->c_segptr, g->n_windows, g->n_c, g->c_order, pair_g, -1.0, rhs_c);
     VB_KERNEL_CHECK();
     return 0;
 }

@@ -98,8 +98,9 @@ class DeviceGraph:
             self.t_rowptr, self.t_time = e(self.n_t + 1, I32), e(E, I32)
             self.t_a, self.t_w = e(E, F64), e(E, F64)
             self.pair_start = e(E + 1, I32)
-            self.c_colptr = e(self.n_c + 1, I32)
-            self.c_w, self.c_perm, self.c_order = e(E, F64), e(E, I32), e(E, I32)
+            self.n_windows = int(lib.vb_ingest_windows(E, self.n_c, tl))
+            self.c_segptr = e(self.n_windows * self.n_c + 1, I32)
+            self.c_w, self.c_order = e(E, F64), e(E, I32)
             self.tile_cam, self.tile_start, self.tile_end = (e(max_tiles + 1, I32), e(max_tiles + 1, I32),
                                                              e(max_tiles + 1, I32))
             self.deg_t, self.deg_c = e(self.n_t, F64), e(self.n_c, F64)
@@ -108,17 +109,17 @@ class DeviceGraph:
                 _ptr(self.cam), _ptr(self.time), _ptr(self.marker), _ptr(R), _ptr(self.k_r), _ptr(self.k_t),
                 _ptr(markerC), n_raw, 1 if round_kr_f32 else 0, _ptr(self.raw_perm), _ptr(self.raw_pair), E,
                 self.n_c, self.n_t, tl, _ptr(self.t_rowptr), _ptr(self.t_cam), _ptr(self.t_time), _ptr(self.t_B),
-                _ptr(self.t_a), _ptr(self.t_w), _ptr(self.pair_start), _ptr(self.c_colptr), _ptr(self.c_time),
-                _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_perm), _ptr(self.c_order), _ptr(self.tile_cam),
+                _ptr(self.t_a), _ptr(self.t_w), _ptr(self.pair_start), _ptr(self.c_segptr), _ptr(self.c_time),
+                _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_order), _ptr(self.tile_cam),
                 _ptr(self.tile_start),
                 _ptr(self.tile_end), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c), _ptr(ws), wsb, _stream()),
                 "vb_ingest_build")
             self.n_tiles = int(ntiles.value)
         del ws, R
         self.cgraph = VbGraph(
-            self.n_c, self.n_t, E, self.n_tiles,
+            self.n_c, self.n_t, E, self.n_tiles, self.n_windows,
             self.t_rowptr.data_ptr(), self.t_cam.data_ptr(), self.t_B.data_ptr(), self.t_w.data_ptr(),
-            self.c_colptr.data_ptr(), self.c_perm.data_ptr(), self.c_time.data_ptr(), self.c_B.data_ptr(),
+            self.c_segptr.data_ptr(), self.c_order.data_ptr(), self.c_time.data_ptr(), self.c_B.data_ptr(),
             self.c_w.data_ptr(),
             self.tile_cam.data_ptr(), self.tile_start.data_ptr(), self.tile_end.data_ptr(),
             self.deg_t.data_ptr(), self.deg_c.data_ptr())
@@ -194,7 +195,7 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
         rhs_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
         check(lib.vb_trans_rhs(C.byref(g.cgraph), _ptr(g.raw_perm), _ptr(g.pair_start), _ptr(g.marker), _ptr(t_cm),
                                _ptr(g.k_t), _ptr(marker_q), _ptr(rot.r_c), _ptr(rot.r_t), _ptr(g.t_time),
-                               _ptr(g.c_perm), _ptr(pair_g), _ptr(d_sorted), _ptr(rhs_c), _ptr(rhs_t), _stream()),
+                               _ptr(pair_g), _ptr(d_sorted), _ptr(rhs_c), _ptr(rhs_t), _stream()),
               "vb_trans_rhs")
         x_c = torch.empty((g.n_c, 3), dtype=F64, device=dev)
         x_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
