@@ -22,4 +22,9 @@ void h_ritz9(const double* G, const double* M, const int* act, double* C, double
     double work[4 * 81];
     vb::ritz9(G, M, act, C, Cp, theta, actP, work);
 }
+void h_ritz9_coop(const double* G, const double* M, const int* act, double* C, double* Cp, double* theta, int* actP) {
+    double work[5 * 81 + 64];
+    int iwork[16];
+    vb::ritz9_coop(G, M, act, C, Cp, theta, actP, work, iwork, 0, 1);
+}
 }

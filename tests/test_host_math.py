@@ -144,7 +144,8 @@ def test_svqb3(lib):
         assert (not (~k).any()) or np.abs(Wn[:, ~k]).max() == 0
 
 
-def test_ritz9_matches_numpy(lib):
+@pytest.mark.parametrize("fn", ["h_ritz9", "h_ritz9_coop"])
+def test_ritz9_matches_numpy(lib, fn):
     rng = np.random.default_rng(7)
     for trial in range(40):
         n = 40
@@ -161,7 +162,7 @@ def test_ritz9_matches_numpy(lib):
         G = S.T @ A @ S
         M = S.T @ S
         C = np.zeros((9, 3)); Cp = np.zeros((9, 3)); th = np.zeros(3); actP = np.zeros(3, np.int32)
-        lib.h_ritz9(P(G), P(M), P(act), P(C), P(Cp), P(th), P(actP))
+        getattr(lib, fn)(P(G), P(M), P(act), P(C), P(Cp), P(th), P(actP))
         k = act.astype(bool)
         import scipy.linalg as sl
         w, v = sl.eigh(G[np.ix_(k, k)], M[np.ix_(k, k)])

@@ -192,4 +192,239 @@ VB_HD void ritz9(const double* Gin, const double* Min, const int* act, double* C
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Cooperative (warp-parallel) version of ritz9: same algorithm, every phase is a loop over
+// independent work items `for (idx = lane; idx < N; idx += nl)` separated by VB_SYNC().  On the
+// device one warp runs it (lane = threadIdx.x, nl = 32, arrays in shared memory) and the 9x9
+// Jacobi eigen-solve uses the round-robin parallel ordering (4 disjoint rotations per round, 9
+// rounds per sweep); on the host the same code runs with nl = 1.  The serial ritz9 above stays
+// as the cross-check of the unit tests.
+#if defined(__CUDA_ARCH__)
+#define VB_SYNC() __syncwarp()
+#else
+#define VB_SYNC() do { } while (0)
+#endif
+
+// round-robin tournament for 9 columns (+1 dummy): round r pairs, -1 = sits out
+VB_HD void rr_pair(int r, int m, int* p, int* q) {
+    // circle method on 10 players, player 9 fixed (dummy), others rotate
+    int a, b;
+    if (m == 0) { a = 9; b = r % 9; }
+    else { a = (r + m) % 9; b = (r + 9 - m) % 9; }
+    if (a == 9 || b == 9) { *p = -1; *q = -1; return; }
+    if (a < b) { *p = a; *q = b; } else { *p = b; *q = a; }
+}
+
+// scratch: work >= 5*81 + 64 doubles ; iwork >= 16 ints
+VB_HD void ritz9_coop(const double* Gin, const double* Min, const int* act, double* C, double* Cp, double* theta,
+                      int* actP, double* work, int* iwork, int lane, int nl) {
+    double* G = work;            // 81
+    double* M = work + 81;       // 81
+    double* R = work + 162;      // 81 Cholesky factor
+    double* Ri = work + 243;     // 81 its inverse
+    double* Q = work + 324;      // 81 temp (G Ri), then eigenvectors
+    double* sc = work + 405;     // small scratch: [0..7] c,s of 4 pairs; [8] scale/floor; [9] dot; [10..18] MZ; [19..27] z; [28..36] lam
+    int* order = iwork;          // 9
+    int* flags = iwork + 9;      // [0] rotations in sweep
+    const int n = 9;
+    for (int idx = lane; idx < 81; idx += nl) {
+        const int i = idx / n, j = idx - n * i;
+        const bool on = act[i] && act[j];
+        double g = on ? 0.5 * (Gin[i * n + j] + Gin[j * n + i]) : 0.0;
+        double m = on ? 0.5 * (Min[i * n + j] + Min[j * n + i]) : 0.0;
+        if (i == j && !act[i]) { m = 1.0; g = VB_BIG; }
+        G[idx] = g; M[idx] = m; R[idx] = 0.0; Ri[idx] = 0.0;
+    }
+    VB_SYNC();
+    // Cholesky M = R^T R (upper R)
+    for (int j = 0; j < n; ++j) {
+        if (lane == 0) {
+            double s = M[j * n + j];
+            for (int k = 0; k < j; ++k) s -= R[k * n + j] * R[k * n + j];
+            R[j * n + j] = sqrt(fmax(s, 1e-300));
+        }
+        VB_SYNC();
+        for (int i = j + 1 + lane; i < n; i += nl) {
+            double v = M[j * n + i];
+            for (int k = 0; k < j; ++k) v -= R[k * n + j] * R[k * n + i];
+            R[j * n + i] = v / R[j * n + j];
+        }
+        VB_SYNC();
+    }
+    // Ri = R^-1 (upper): one column per work item
+    for (int j = lane; j < n; j += nl) {
+        Ri[j * n + j] = 1.0 / R[j * n + j];
+        for (int i = j - 1; i >= 0; --i) {
+            double s = 0.0;
+            for (int k = i + 1; k <= j; ++k) s += R[i * n + k] * Ri[k * n + j];
+            Ri[i * n + j] = -s / R[i * n + i];
+        }
+    }
+    VB_SYNC();
+    // Q = G Ri ; G = Ri^T Q ; symmetrise
+    for (int idx = lane; idx < 81; idx += nl) {
+        const int i = idx / n, j = idx - n * i;
+        double s = 0.0;
+        for (int k = 0; k <= j; ++k) s += G[i * n + k] * Ri[k * n + j];
+        Q[idx] = s;
+    }
+    VB_SYNC();
+    for (int idx = lane; idx < 81; idx += nl) {
+        const int i = idx / n, j = idx - n * i;
+        double s = 0.0;
+        for (int k = 0; k <= i; ++k) s += Ri[k * n + i] * Q[k * n + j];
+        G[idx] = s;
+    }
+    VB_SYNC();
+    for (int idx = lane; idx < 81; idx += nl) {
+        const int i = idx / n, j = idx - n * i;
+        if (i < j) { const double s = 0.5 * (G[i * n + j] + G[j * n + i]); R[i * n + j] = s; R[j * n + i] = s; }
+        else if (i == j) R[idx] = G[idx];
+    }
+    VB_SYNC();
+    for (int idx = lane; idx < 81; idx += nl) {
+        const int i = idx / n, j = idx - n * i;
+        G[idx] = R[idx];
+        Q[idx] = (i == j) ? 1.0 : 0.0;
+    }
+    VB_SYNC();
+    // scale for the absolute "negligible" floor (masked columns carry VB_BIG and do not count)
+    if (lane == 0) {
+        double scale = 0.0;
+        for (int i = 0; i < 81; ++i) { const double v = fabs(G[i]); if (v < 1e-2 * VB_BIG && v > scale) scale = v; }
+        sc[8] = 1e-19 * scale + 1e-300;
+    }
+    VB_SYNC();
+    const double floor_abs = sc[8];
+    // parallel-ordered cyclic Jacobi
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        if (lane == 0) flags[0] = 0;
+        VB_SYNC();
+        for (int r = 0; r < 9; ++r) {
+            for (int m = lane; m < 5; m += nl) {
+                int p, q;
+                rr_pair(r, m, &p, &q);
+                double c = 1.0, s = 0.0;
+                if (p >= 0) {
+                    const double apq = G[p * n + q], app = G[p * n + p], aqq = G[q * n + q];
+                    if (!(fabs(apq) <= floor_abs || fabs(apq) <= 1e-17 * sqrt(fabs(app) * fabs(aqq)))) {
+                        const double z = (aqq - app) / (2.0 * apq);
+                        const double t = (z >= 0.0 ? 1.0 : -1.0) / (fabs(z) + sqrt(1.0 + z * z));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = c * t;
+                        flags[1 + m] = 1;
+                    } else flags[1 + m] = 0;
+                } else flags[1 + m] = 0;
+                sc[2 * m] = c; sc[2 * m + 1] = s;
+            }
+            VB_SYNC();
+            // columns p,q of G and Q  (item = pair m, row i)
+            for (int idx = lane; idx < 5 * 9; idx += nl) {
+                const int m = idx / 9, i = idx - 9 * m;
+                int p, q;
+                rr_pair(r, m, &p, &q);
+                if (p < 0) continue;
+                const double c = sc[2 * m], s = sc[2 * m + 1];
+                const double gp = G[i * n + p], gq = G[i * n + q];
+                G[i * n + p] = c * gp - s * gq;
+                G[i * n + q] = s * gp + c * gq;
+                const double qp = Q[i * n + p], qq = Q[i * n + q];
+                Q[i * n + p] = c * qp - s * qq;
+                Q[i * n + q] = s * qp + c * qq;
+            }
+            VB_SYNC();
+            // rows p,q of G  (item = pair m, column j)
+            for (int idx = lane; idx < 5 * 9; idx += nl) {
+                const int m = idx / 9, j = idx - 9 * m;
+                int p, q;
+                rr_pair(r, m, &p, &q);
+                if (p < 0) continue;
+                const double c = sc[2 * m], s = sc[2 * m + 1];
+                const double gp = G[p * n + j], gq = G[q * n + j];
+                G[p * n + j] = c * gp - s * gq;
+                G[q * n + j] = s * gp + c * gq;
+            }
+            VB_SYNC();
+            for (int m = lane; m < 5; m += nl) {
+                int p, q;
+                rr_pair(r, m, &p, &q);
+                if (p >= 0) { G[p * n + q] = 0.0; G[q * n + p] = 0.0; if (flags[1 + m]) flags[0] = 1; }
+            }
+            VB_SYNC();
+        }
+        if (flags[0] == 0) break;
+    }
+    // sort ascending by rank counting
+    double* lam = sc + 28;
+    for (int i = lane; i < n; i += nl) lam[i] = G[i * n + i];
+    VB_SYNC();
+    for (int i = lane; i < n; i += nl) {
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (lam[j] < lam[i]) || (lam[j] == lam[i] && j < i);
+        order[rank] = i;
+    }
+    VB_SYNC();
+    for (int idx = lane; idx < 27; idx += nl) {
+        const int i = idx / 3, j = idx - 3 * i;
+        const int col = order[j];
+        double s = 0.0;
+        for (int k = i; k < n; ++k) s += Ri[i * n + k] * Q[k * n + col];
+        C[idx] = s;
+        if (i == 0) theta[j] = lam[col];
+    }
+    VB_SYNC();
+    // new search directions: Z = [0; C_w; C_p], M-orthogonalised against C and the accepted
+    // columns (modified Gram-Schmidt, twice), dropped when nothing is left
+    double* MZ = sc + 10;
+    double* z = sc + 19;
+    for (int j = 0; j < 3; ++j) {
+        for (int i = lane; i < n; i += nl) z[i] = (i < 3) ? 0.0 : C[i * 3 + j];
+        VB_SYNC();
+        double n0 = 0.0;
+        for (int pass = 0; pass < 3; ++pass) {       // pass 0: norm before; 1,2: projections
+            for (int cidx = 0; cidx < ((pass == 0) ? 1 : 3 + j); ++cidx) {
+                for (int i = lane; i < n; i += nl) {
+                    double s = 0.0;
+                    for (int k = 0; k < n; ++k) s += M[i * n + k] * z[k];
+                    MZ[i] = s;
+                }
+                VB_SYNC();
+                if (pass == 0) {
+                    if (lane == 0) { double s = 0.0; for (int i = 0; i < n; ++i) s += z[i] * MZ[i]; sc[9] = sqrt(fmax(s, 0.0)); }
+                    VB_SYNC();
+                    n0 = sc[9];
+                    continue;
+                }
+                const double* b = (cidx < 3) ? C : Cp;
+                const int bc = (cidx < 3) ? cidx : cidx - 3;
+                const bool use = (cidx < 3) || actP[bc];
+                if (lane == 0) { double s = 0.0; if (use) for (int i = 0; i < n; ++i) s += b[i * 3 + bc] * MZ[i]; sc[9] = s; }
+                VB_SYNC();
+                const double dot = sc[9];
+                for (int i = lane; i < n; i += nl) z[i] -= dot * b[i * 3 + bc];
+                VB_SYNC();
+            }
+        }
+        for (int i = lane; i < n; i += nl) {
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += M[i * n + k] * z[k];
+            MZ[i] = s;
+        }
+        VB_SYNC();
+        if (lane == 0) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s += z[i] * MZ[i];
+            const double nz = sqrt(fmax(s, 0.0));
+            const bool keep = (nz > 1e-8 * fmax(n0, 1e-300)) && (nz > 1e-150);
+            actP[j] = keep ? 1 : 0;
+            sc[9] = keep ? 1.0 / nz : 0.0;
+        }
+        VB_SYNC();
+        const double inz = sc[9];
+        for (int i = lane; i < n; i += nl) Cp[i * 3 + j] = z[i] * inz;
+        VB_SYNC();
+    }
+}
+
 }  // namespace vb

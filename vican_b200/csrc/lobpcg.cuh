@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     cg::grid_group grid = cg::this_grid();
     __shared__ double red_sm[8 * 27];
     __shared__ double tot[LOB_NRED];
-    __shared__ double Gm[81], Mm[81], Cx[27], Cp[27], work[4 * 81];
+    __shared__ double Gm[81], Mm[81], Cx[27], Cp[27], work[5 * 81 + 64];
+    __shared__ int iwork[16];
     __shared__ double theta_s[3], H[18], T[9];
     __shared__ int act_s[9], actP_s[3], actW_s[3], conv_s;
 
@@ -154,22 +155,25 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     grid_combine(base1, 109, tot);
 
     // ---------------- stage 2: Rayleigh-Ritz (redundant per CTA, deterministic) ------------
-    if (threadIdx.x == 0) {
-        int blk = 0;
-        for (int a = 0; a < 3; ++a)
-            for (int b = a; b < 3; ++b, ++blk)
-                for (int j = 0; j < 3; ++j)
-                    for (int jp = 0; jp < 3; ++jp) {
-                        const double g = tot[9 * blk + 3 * j + jp], m = tot[54 + 9 * blk + 3 * j + jp];
-                        Gm[(3 * a + j) * 9 + 3 * b + jp] = g;
-                        Mm[(3 * a + j) * 9 + 3 * b + jp] = m;
-                        if (a != b) {
-                            Gm[(3 * b + jp) * 9 + 3 * a + j] = g;
-                            Mm[(3 * b + jp) * 9 + 3 * a + j] = m;
-                        }
-                    }
-        for (int i = 0; i < 9; ++i) act_s[i] = (i < 3) ? 1 : (p.first ? 0 : (p.small[SM_ACT + i] != 0.0));
-        ritz9(Gm, Mm, act_s, Cx, Cp, theta_s, actP_s, work);
+    // one warp per CTA: warp-cooperative 9x9 solve (parallel-ordered Jacobi), dense_small.cuh
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int idx = lane; idx < 54; idx += 32) {
+            const int blk = idx / 9, e9 = idx - 9 * blk, j = e9 / 3, jp = e9 - 3 * j;
+            // upper blocks in the order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2)
+            const int a = (blk < 3) ? 0 : ((blk < 5) ? 1 : 2);
+            const int b = (blk < 3) ? blk : ((blk < 5) ? blk - 2 : 2);
+            const double g = tot[idx], m = tot[54 + idx];
+            Gm[(3 * a + j) * 9 + 3 * b + jp] = g;
+            Mm[(3 * a + j) * 9 + 3 * b + jp] = m;
+            if (a != b) {
+                Gm[(3 * b + jp) * 9 + 3 * a + j] = g;
+                Mm[(3 * b + jp) * 9 + 3 * a + j] = m;
+            }
+        }
+        for (int i = lane; i < 9; i += 32) act_s[i] = (i < 3) ? 1 : (p.first ? 0 : (p.small[SM_ACT + i] != 0.0));
+        __syncwarp();
+        ritz9_coop(Gm, Mm, act_s, Cx, Cp, theta_s, actP_s, work, iwork, lane, 32);
     }
     __syncthreads();
 
