@@ -169,7 +169,8 @@ int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t);
  * (accurate mode; not the reference iteration).  x_c [n_c][3], x_t [n_t][3]. */
 int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t,
                 double rtol, int64_t maxiter, int jacobi, int32_t* h_iters, void* workspace,
-                int64_t workspace_bytes, vb_allreduce_fn allreduce, void* allreduce_ctx, void* stream);
+                int64_t workspace_bytes, vb_allreduce_fn allreduce, void* allreduce_ctx,
+                int owns_camera_diagonal /* 1 on a single GPU and on rank 0 of a sharded run */, void* stream);
 int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw);
 /* LSQR on J x = t~ replaying scipy.sparse.linalg.lsqr defaults (bipgo.py:480: damp 0,
  * atol = btol = 1e-6, conlim 1e8, iter_lim = 2 * 3N).  Rows are the raw detections in sorted

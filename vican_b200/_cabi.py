@@ -76,7 +76,8 @@ SIGNATURES = {
                                  C.POINTER(VbSo3Stats), VP]),
     "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "vb_trans_cg_workspace_bytes": (I64, [I64, I64]),
-    "vb_trans_cg": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, F64, I64, C.c_int, c_i32p, VP, I64, VP, VP, VP]),
+    "vb_trans_cg": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, F64, I64, C.c_int, c_i32p, VP, I64, VP, VP, C.c_int,
+                              VP]),
     "vb_trans_lsqr_workspace_bytes": (I64, [I64, I64, I64]),
     "vb_trans_lsqr": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, I64, VP, VP, F64, F64, F64, I64,
                                 c_i32p, c_i32p, VP, I64, VP]),

@@ -87,7 +87,7 @@ class EdgeTable:
 
 
 def _solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: Optional[str], mode: str = "parity",
-                 tol: float = 1e-11):
+                 tol: float = 1e-13):
     t0 = _time.perf_counter()
     g = _solver.DeviceGraph(tab.cam_idx, tab.time_idx, tab.marker_idx, tab.R, tab.k_r, tab.k_t, tab.markerC,
                             tab.n_c, tab.n_t, round_kr_f32=tab.round_kr_f32)

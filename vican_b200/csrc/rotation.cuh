@@ -215,10 +215,15 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         VB_RC(launch_lobpcg_step(lp, st));
         S->lobpcg_steps++; S->kernel_launches++;
         int inner = 1;
+        double hist[3] = {1e300, 1e300, 1e300};   // residuals of the last three steps (stagnation guard)
         for (;;) {
             VB_CHECK(cudaMemcpyAsync(hs, w.small, SM_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
             VB_CHECK(cudaStreamSynchronize(st));
             if (hs[SM_CONV] != 0.0) break;
+            // rounding floor reached: the residual stopped shrinking although it is already tiny
+            const double rmax = fmax(hs[SM_RESN], fmax(hs[SM_RESN + 1], hs[SM_RESN + 2]));
+            if (rmax < 1e-9 * hs[SM_ANORM] && rmax > 0.5 * hist[0]) break;
+            hist[0] = hist[1]; hist[1] = hist[2]; hist[2] = rmax;
             if (inner >= max_inner) { S->stalled_outer++; status = VB_STATUS_EIG_STALLED; break; }
             VB_RC(time_pass(0, w.W, w.Wt));
             VB_RC(cam_pass(w.Wt, w.Y));

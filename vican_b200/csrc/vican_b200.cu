@@ -233,9 +233,9 @@ int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_cg(
 
 int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t, double rtol,
                 int64_t maxiter, int jacobi, int32_t* h_iters, void* workspace, int64_t workspace_bytes,
-                vb_allreduce_fn allreduce, void* allreduce_ctx, void* stream) {
+                vb_allreduce_fn allreduce, void* allreduce_ctx, int owns_camera_diagonal, void* stream) {
     return trans_cg(g, rhs_c, rhs_t, x_c, x_t, rtol, maxiter, jacobi, h_iters, workspace, workspace_bytes, allreduce,
-                    allreduce_ctx, (cudaStream_t)stream);
+                    allreduce_ctx, owns_camera_diagonal, (cudaStream_t)stream);
 }
 
 int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw) {

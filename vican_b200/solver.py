@@ -147,7 +147,7 @@ class RotationResult:
                 self.r_t.view(-1, 3, 3).transpose(1, 2).contiguous())
 
 
-def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-11, max_inner: int = 200,
+def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner: int = 200,
                     comm: Optional[Comm] = None) -> RotationResult:
     lib = _cabi.lib()
     dev = g.device
@@ -223,7 +223,8 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
             rc = lib.vb_trans_cg(C.byref(g.cgraph), _ptr(rhs_c), _ptr(rhs_t), _ptr(x_c), _ptr(x_t), rtol,
                                  10 * n_unknowns, jacobi, C.byref(iters), _ptr(ws), wsb,
                                  lib.vb_nccl_allreduce_fn() if comm is not None else None,
-                                 comm.ctx if comm is not None else None, _stream())
+                                 comm.ctx if comm is not None else None,
+                                 1 if (comm is None or comm.rank == 0) else 0, _stream())
             if rc == 1:
                 raise ConvergenceError("conjugate gradient did not converge (reference: assert exit_code == 0)")
             check(rc, "vb_trans_cg")
@@ -255,7 +256,7 @@ class SolveResult:
 
 
 def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int, n_t: int, maxiter: int,
-                 lsqr_solver: str = "conjugate_gradient", mode: str = "parity", tol: float = 1e-11,
+                 lsqr_solver: str = "conjugate_gradient", mode: str = "parity", tol: float = 1e-13,
                  comm: Optional[Comm] = None, round_kr_f32: bool = False, to_host: bool = False,
                  graph: Optional[DeviceGraph] = None) -> SolveResult:
     """Array fast path of ``bipartite_se3sync`` (no dicts, no Python callables): raw detections
