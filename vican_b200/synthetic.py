@@ -222,10 +222,11 @@ def to_edge_dict(g: SyntheticGraph, se3_cls) -> Tuple[Dict, Optional[Dict]]:
 
 
 def corner_area(corners: np.ndarray) -> float:
-    """Shoelace area of the detected marker quadrilateral -- the quantity the
-    notebook's noise models are built from (main.ipynb cells 3 and 7)."""
-    x, y = corners[:, 0], corners[:, 1]
-    return float(0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1))))
+    """Shoelace area of the detected marker quadrilateral -- the quantity the notebook's noise
+    models are built from (main.ipynb cells 3 and 7).  Plain Python arithmetic: it is called once
+    or twice per detection by the synthetic noise models."""
+    (x0, y0), (x1, y1), (x2, y2), (x3, y3) = corners.tolist()
+    return 0.5 * abs((x0 * y1 - x1 * y0) + (x1 * y2 - x2 * y1) + (x2 * y3 - x3 * y2) + (x3 * y0 - x0 * y3))
 
 
 def default_callables() -> Tuple[Callable, Callable, Callable]:
