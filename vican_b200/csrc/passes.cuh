@@ -146,9 +146,55 @@ __device__ __forceinline__ double reduce_scatter9(const double (&v)[9], int lane
     return s;
 }
 
+struct Item {
+    int seg, a, b;
+    bool last, valid;
+};
+
+// item loads: block rows (LDS) + far-endpoint indices (LDS) + 256-bit row gathers, all issued back to back
+template <bool TR>
+__device__ __forceinline__ void item_load(const unsigned char* bufp, const double* __restrict__ G, const Item& it, int e,
+                                          int k, double (&b)[5][3], double (&x)[5][3]) {
+    const double* sB = reinterpret_cast<const double*>(bufp);
+    const int* sI = reinterpret_cast<const int*>(bufp + BUF_B_BYTES);
+    const int offB = it.a - (it.a & ~1), offI = it.a - (it.a & ~3), n_e = it.b - it.a;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+        const int off = EDGES_PER_ROUND * u + e;
+        b[u][0] = b[u][1] = b[u][2] = 0.0;
+        x[u][0] = x[u][1] = x[u][2] = 0.0;
+        if ((e < EDGES_PER_ROUND) && (off < n_e)) {
+            const int node = sI[offI + off];
+            const double* pb = sB + 9 * (offB + off) + (TR ? 3 * k : k);
+            b[u][0] = pb[0];
+            b[u][1] = pb[TR ? 1 : 3];
+            b[u][2] = pb[TR ? 2 : 6];
+            ld_row256(G + GSTRIDE * (size_t)node + 4 * k, x[u][0], x[u][1], x[u][2]);
+        }
+    }
+}
+
+__device__ __forceinline__ void item_fma(const Item& it, const double (&b)[5][3], const double (&x)[5][3], double (&acc)[9]) {
+    const int n_e = it.b - it.a;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+        if (EDGES_PER_ROUND * u < n_e) {   // warp-uniform: skip empty tail rounds
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[3 * a + j] = fma(b[u][a], x[u][j], acc[3 * a + j]);
+        }
+    }
+}
+
 // MODE 0: out_t = Lambda_T[t] * sum B^T X   (padded rows)   -- L-apply / primal multiply (bipgo.py:300)
 // MODE 1: out_t = sum B^T X                 (padded rows)   -- dual gather Y = P^T r_c (bipgo.py:318)
 // MODE 2: Y_c  += sum over tile of B W      (compact 9, fp64 atomics per TILE, not per edge)
+//
+// Per-warp software pipeline over work items (<= 50 edges of one segment):
+//   FMA(item k)  ->  TMA issue(item k+2)  ->  wait + loads(item k+1)  ->  epilogue(segment of k, if it ends)
+// so the segment reduction / store overlaps the gather round trip of the next item and the TMA copy
+// of an item has one full iteration to land.
 template <int MODE, int CTAS>
 __global__ void __launch_bounds__(PASS_THREADS, CTAS)
 edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ idx,
@@ -174,71 +220,74 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
     const uint64_t pf = policy_evict_first();
     const int e = lane / 3, k = lane - 3 * e;   // lanes 30, 31: e = 10 -> idle in the loop, zero in the reduction
 
-    auto issue = [&](int a, int b, int buf) {   // elected lane only
-        const int a0 = a & ~1, b1 = (b + 1) & ~1;
-        const int a0i = a & ~3, b1i = (b + 3) & ~3;
-        const uint32_t nbB = (uint32_t)(b1 - a0) * 72u, nbI = (uint32_t)(b1i - a0i) * 4u;
-        unsigned char* dst = wbuf + buf * BUF_BYTES;
-        mbar_expect_tx(&bars[buf], nbB + nbI);
-        bulk_g2s(dst, B + 9 * (size_t)a0, nbB, &bars[buf], pf);
-        bulk_g2s(dst + BUF_B_BYTES, idx + a0i, nbI, &bars[buf], pf);
+    // ---- item iterator (warp-uniform).  Row pointers are fetched two segments ahead of their use.
+    int it_seg = warp, it_s = __ldg(seg_ptr + warp), it_e = __ldg(seg_ptr + warp + 1), it_pos = it_s;
+    bool it_started = false, it_valid = true;
+    int n1_seg = warp + nwarps, n1_s = 0, n1_e = 0, n2_s = 0, n2_e = 0;
+    if (n1_seg < n_seg) { n1_s = __ldg(seg_ptr + n1_seg); n1_e = __ldg(seg_ptr + n1_seg + 1); }
+    if (n1_seg + nwarps < n_seg) { n2_s = __ldg(seg_ptr + n1_seg + nwarps); n2_e = __ldg(seg_ptr + n1_seg + nwarps + 1); }
+    auto next_item = [&]() -> Item {
+        Item it;
+        it.seg = 0; it.a = 0; it.b = 0; it.last = false; it.valid = false;
+        if (!it_valid) return it;
+        if (it_started && it_pos >= it_e) {
+            if (n1_seg >= n_seg) { it_valid = false; return it; }
+            it_seg = n1_seg; it_s = n1_s; it_e = n1_e; it_pos = it_s; it_started = false;
+            n1_seg += nwarps; n1_s = n2_s; n1_e = n2_e;
+            if (n1_seg + nwarps < n_seg) { n2_s = __ldg(seg_ptr + n1_seg + nwarps); n2_e = __ldg(seg_ptr + n1_seg + nwarps + 1); }
+        }
+        it.seg = it_seg; it.a = it_pos; it.b = min(it_pos + ITEM_EDGES, it_e);
+        it_pos = it.b; it_started = true;
+        it.last = (it.b >= it_e); it.valid = true;
+        return it;
+    };
+    auto issue = [&](const Item& it, int buf) {   // whole warp calls; one elected lane issues
+        if (!it.valid || it.b <= it.a) return;
+        __syncwarp();
+        if (lane == 0) {
+            const int a0 = it.a & ~1, b1 = (it.b + 1) & ~1;
+            const int a0i = it.a & ~3, b1i = (it.b + 3) & ~3;
+            const uint32_t nbB = (uint32_t)(b1 - a0) * 72u, nbI = (uint32_t)(b1i - a0i) * 4u;
+            unsigned char* dst = wbuf + buf * BUF_BYTES;
+            mbar_expect_tx(&bars[buf], nbB + nbI);
+            bulk_g2s(dst, B + 9 * (size_t)a0, nbB, &bars[buf], pf);
+            bulk_g2s(dst + BUF_B_BYTES, idx + a0i, nbI, &bars[buf], pf);
+        }
+    };
+    uint32_t phases = 0;
+    auto wait_buf = [&](const Item& it, int buf) {
+        if (!it.valid || it.b <= it.a) return;
+        mbar_wait(&bars[buf], (phases >> buf) & 1u);
+        phases ^= (1u << buf);
     };
 
-    int cseg = warp;
-    int cs = __ldg(seg_ptr + cseg), ce = __ldg(seg_ptr + cseg + 1);
-    int ca = cs, cb = min(cs + ITEM_EDGES, ce);
-    int nseg = cseg + nwarps, ns = 0, ne = 0;   // row pointers of the next segment, fetched one segment early
-    if (nseg < n_seg) { ns = __ldg(seg_ptr + nseg); ne = __ldg(seg_ptr + nseg + 1); }
-    uint32_t phase0 = 0, phase1 = 0;
-    int n_issued = 0, cur_buf = 0;
-    bool cur_issued = false;
-    if (cb > ca) {
-        if (lane == 0) issue(ca, cb, 0);
-        cur_issued = true; cur_buf = 0; n_issued = 1;
-    }
-    // Lambda_T row of the current segment for the epilogue, fetched early (latency hidden)
-    double lam0 = 0.0, lam1 = 0.0, lam2 = 0.0;
-    if (MODE == 0 && lane < 9) {
-        const double* L = lamT + 9 * (size_t)cseg + 3 * (lane / 3);
-        lam0 = L[0]; lam1 = L[1]; lam2 = L[2];
-    }
+    double bq[5][3], xq[5][3];
+    double lamC[3] = {0.0, 0.0, 0.0}, lamN[3] = {0.0, 0.0, 0.0};
+    auto load = [&](const Item& it, int buf, double (&lam)[3]) {
+        if (!it.valid) return;
+        item_load<TR>(wbuf + buf * BUF_BYTES, G, it, e, k, bq, xq);
+        if (MODE == 0 && it.last && lane < 9) {   // Lambda_T row for this segment's epilogue
+            const double* L = lamT + 9 * (size_t)it.seg + 3 * (lane / 3);
+            lam[0] = L[0]; lam[1] = L[1]; lam[2] = L[2];
+        }
+    };
     double acc[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) acc[i] = 0.0;
 
-    for (;;) {
-        // ---- look ahead: next chunk of this segment, or the head of the next segment
-        bool has_next = true, next_new_seg = false;
-        int na = 0, nb = 0;
-        if (cb < ce) { na = cb; nb = min(cb + ITEM_EDGES, ce); }
-        else if (nseg < n_seg) { na = ns; nb = min(ns + ITEM_EDGES, ne); next_new_seg = true; }
-        else has_next = false;
-        bool next_issued = false;
-        int next_buf = 0;
-        if (has_next && nb > na) {
-            next_buf = n_issued & 1;
-            __syncwarp();   // every lane is done reading that buffer (item before the current one)
-            if (lane == 0) issue(na, nb, next_buf);
-            next_issued = true;
-            ++n_issued;
-        }
-        // ---- consume the current item from shared memory
-        if (cur_issued) {
-            if (cur_buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
-            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
-            const unsigned char* bufp = wbuf + cur_buf * BUF_BYTES;
-            const double* sB = reinterpret_cast<const double*>(bufp);
-            const int* sI = reinterpret_cast<const int*>(bufp + BUF_B_BYTES);
-            const int offB = ca - (ca & ~1), offI = ca - (ca & ~3);
-            const int n_e = cb - ca;
-            // all gathers of the item are issued back to back (one exposed L2 round trip per item)
-            constexpr int R = EDGES_PER_ROUND;
-            if (n_e > 3 * R) edge_rounds<TR, 5>(sB, sI, G, offB, offI, 0, n_e, e, k, acc);
-            else if (n_e > R) edge_rounds<TR, 3>(sB, sI, G, offB, offI, 0, n_e, e, k, acc);
-            else edge_rounds<TR, 1>(sB, sI, G, offB, offI, 0, n_e, e, k, acc);
-        }
-        // ---- segment finished: combine the 30 private sums and emit
-        if (cb >= ce) {
+    Item i0 = next_item(), i1 = next_item(), i2;
+    issue(i0, 0);
+    issue(i1, 1);
+    wait_buf(i0, 0);
+    load(i0, 0, lamC);
+    int buf0 = 0;
+    while (i0.valid) {
+        item_fma(i0, bq, xq, acc);          // registers of item k are free after this
+        i2 = next_item();
+        issue(i2, buf0);                     // item k's stage is free (all its LDS fed the FMAs above)
+        wait_buf(i1, buf0 ^ 1);
+        load(i1, buf0 ^ 1, lamN);            // gathers of item k+1 in flight during the epilogue below
+        if (i0.last) {                       // segment finished: combine the 30 private sums and emit
             int vidx;
             const double tot = reduce_scatter9(acc, lane, &vidx);
             const bool holder = ((lane & 1) == 0) && (vidx < 9);
@@ -247,29 +296,21 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
                 __syncwarp();
                 if (lane < 9) {
                     const int a = lane / 3, j = lane - 3 * a;
-                    out[GSTRIDE * (size_t)cseg + 4 * a + j] = lam0 * scratch[j] + lam1 * scratch[3 + j] + lam2 * scratch[6 + j];
+                    out[GSTRIDE * (size_t)i0.seg + 4 * a + j] =
+                        lamC[0] * scratch[j] + lamC[1] * scratch[3 + j] + lamC[2] * scratch[6 + j];
                 }
                 __syncwarp();
             } else if (MODE == 1) {
-                if (holder) out[GSTRIDE * (size_t)cseg + 4 * (vidx / 3) + (vidx % 3)] = tot;
+                if (holder) out[GSTRIDE * (size_t)i0.seg + 4 * (vidx / 3) + (vidx % 3)] = tot;
             } else {
-                if (holder) atomicAdd(out + 9 * (size_t)__ldg(seg_node + cseg) + vidx, tot);
+                if (holder) atomicAdd(out + 9 * (size_t)__ldg(seg_node + i0.seg) + vidx, tot);
             }
 #pragma unroll
             for (int i = 0; i < 9; ++i) acc[i] = 0.0;
         }
-        if (!has_next) break;
-        // ---- advance
-        if (next_new_seg) {
-            cseg = nseg; cs = ns; ce = ne;
-            nseg += nwarps;
-            if (nseg < n_seg) { ns = __ldg(seg_ptr + nseg); ne = __ldg(seg_ptr + nseg + 1); }
-            if (MODE == 0 && lane < 9) {
-                const double* L = lamT + 9 * (size_t)cseg + 3 * (lane / 3);
-                lam0 = L[0]; lam1 = L[1]; lam2 = L[2];
-            }
-        }
-        ca = na; cb = nb; cur_issued = next_issued; cur_buf = next_buf;
+        if (MODE == 0 && i1.valid && i1.last) { lamC[0] = lamN[0]; lamC[1] = lamN[1]; lamC[2] = lamN[2]; }
+        i0 = i1; i1 = i2;
+        buf0 ^= 1;
     }
 }
 
@@ -295,19 +336,10 @@ inline int pass_grid(int64_t n_segments, int ctas_per_sm) {
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-inline int pass_ctas() {
-    static int v = 0;
-    if (v == 0) {
-        const char* e = getenv("VB_PASS_CTAS");
-        v = e ? atoi(e) : PASS_CTAS_PER_SM;
-        if (v < 4 || v > 6) v = PASS_CTAS_PER_SM;
-    }
-    return v;
-}
-
-template <int MODE, int CTAS>
-inline int launch_edge_pass_c(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
-                              const double* lamT, double* out, int64_t n_seg, cudaStream_t st) {
+template <int MODE>
+inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
+                            const double* lamT, double* out, int64_t n_seg, cudaStream_t st) {
+    constexpr int CTAS = PASS_CTAS_PER_SM;   // 5 or 6 CTAs / SM (80-96 registers) measured slower, see profiles/
     static bool attr_set = false;
     if (!attr_set) {
         VB_CHECK(cudaFuncSetAttribute(edge_pass_kernel<MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
@@ -316,16 +348,6 @@ inline int launch_edge_pass_c(const int* seg_ptr, const int* seg_node, const int
     edge_pass_kernel<MODE, CTAS><<<pass_grid(n_seg, CTAS), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg);
     VB_KERNEL_CHECK();
     return 0;
-}
-
-template <int MODE>
-inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
-                            const double* lamT, double* out, int64_t n_seg, cudaStream_t st) {
-    switch (pass_ctas()) {
-        case 5: return launch_edge_pass_c<MODE, 5>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st);
-        case 6: return launch_edge_pass_c<MODE, 6>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st);
-        default: return launch_edge_pass_c<MODE, 4>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st);
-    }
 }
 
 // NOTE: idx must be readable up to index ((E+3)&~3)-1 and B up to edge ((E+1)&~1)-1 (the bulk
