@@ -146,23 +146,25 @@ __global__ void tile_fill_kernel(const int* __restrict__ colptr, const int* __re
     }
 }
 
-// key = ((window(time) * n_c + cam) * n_t + time): camera-pass order.  Tiles of all cameras that
-// fall in the same time window are adjacent in the stream, so the W records gathered by
-// concurrently running warps come from one window of W (L2 resident) instead of all of it.
+// key = window(time) * n_c + cam: camera-pass order.  The input (aggregated pairs) is already
+// sorted by (time, camera) and the radix sort is stable, so the result is ordered by
+// (window, camera, time) with only log2(n_win * n_c) key bits.  Tiles of all cameras that fall in
+// the same time window are adjacent in the stream, so the W records gathered by concurrently
+// running warps come from one window of W (L2 resident) instead of all of it.
 __global__ void make_window_keys_kernel(const int* __restrict__ cam, const int* __restrict__ time, int64_t n_c, int64_t n_t,
                                         int64_t n_win, uint64_t* __restrict__ keys, int* __restrict__ vals, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t t = (uint64_t)time[i];
     const uint64_t win = t * (uint64_t)n_win / (uint64_t)n_t;
-    keys[i] = (win * (uint64_t)n_c + (uint64_t)cam[i]) * (uint64_t)n_t + t;
+    keys[i] = win * (uint64_t)n_c + (uint64_t)cam[i];
     vals[i] = (int)i;
 }
 
-__global__ void window_seg_kernel(const uint64_t* __restrict__ keys_sorted, int64_t n_t, int* __restrict__ seg, int64_t n) {
+__global__ void window_seg_kernel(const uint64_t* __restrict__ keys_sorted, int* __restrict__ seg, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    seg[i] = (int)(keys_sorted[i] / (uint64_t)n_t);
+    seg[i] = (int)keys_sorted[i];
 }
 
 // warp per camera: out[c] = sum over the camera's (window, camera) runs of a[order[i]] -- the

@@ -149,8 +149,8 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     make_window_keys_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, t_time, n_c, n_t, n_win, w.keys_a, w.vals_a, E);
     size_t tb = w.cub_bytes;
     VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
-                                             c_order, (int)E, 0, key_bits(n_c * n_win, n_t), st));
-    window_seg_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.keys_b, n_t, w.tmp_a, E);
+                                             c_order, (int)E, 0, key_bits(n_c, n_win), st));
+    window_seg_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.keys_b, w.tmp_a, E);
     seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.tmp_a, nullptr, c_segptr, E, n_seg);
     cam_runs_sum_kernel<<<ing_grid(n_c * 32), ING_THREADS, 0, st>>>(c_segptr, n_win, n_c, c_order, t_a, deg_c);
     gather_cam_sorted_kernel<<<ing_grid(9 * E), ING_THREADS, 0, st>>>(c_order, t_time, t_B, t_w, c_time, c_B, c_w, E);

@@ -39,6 +39,35 @@ def _dev(x, dtype, device):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device, non_blocking=True)
 
 
+class HostUpload:
+    """Host -> device upload of the raw detection arrays on a side stream, in the order the
+    pipeline consumes them (indices first: the key sort starts while the 72-byte rotation blocks
+    are still crossing PCIe; translations last: they are only needed after the rotation stage).
+    ``get(name)`` makes the CURRENT stream wait for that array's copy and returns the tensor."""
+
+    ORDER = ("cam", "time", "marker", "k_r", "k_t", "R", "t")
+
+    def __init__(self, arrays: dict, dtypes: dict, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._t, self._ev = {}, {}
+        cur = torch.cuda.current_stream(device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for name in self.ORDER:
+                if name not in arrays:
+                    continue
+                t = _dev(arrays[name], dtypes[name], device)
+                t.record_stream(cur)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self._t[name], self._ev[name] = t, ev
+
+    def get(self, name):
+        torch.cuda.current_stream(self.device).wait_event(self._ev[name])
+        return self._t[name]
+
+
 @dataclasses.dataclass
 class Comm:
     """NCCL communicator handle of the extension (edge-sharded multi-GPU runs)."""
@@ -58,17 +87,17 @@ class DeviceGraph:
     """Device-resident aggregated bipartite graph (time-sorted CSR + camera-sorted CSC)."""
 
     def __init__(self, cam, time, marker, R, k_r, k_t, markerC, n_c: int, n_t: int,
-                 round_kr_f32: bool = False, device=None, tile_len: Optional[int] = None):
+                 round_kr_f32: bool = False, device=None, tile_len: Optional[int] = None,
+                 upload: Optional[HostUpload] = None):
         lib = _cabi.lib()
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device = dev
         self.n_c, self.n_t = int(n_c), int(n_t)
-        self.cam = _dev(cam, I32, dev)
-        self.time = _dev(time, I32, dev)
-        self.marker = _dev(marker, I32, dev)
-        R = _dev(R, F64, dev).reshape(-1, 9)
-        self.k_r = _dev(k_r, F64, dev)
-        self.k_t = _dev(k_t, F64, dev)
+        if upload is not None:        # arrays are crossing PCIe on a side stream: wait only for the indices now
+            self.cam, self.time = upload.get("cam"), upload.get("time")
+        else:
+            self.cam = _dev(cam, I32, dev)
+            self.time = _dev(time, I32, dev)
         markerC = _dev(markerC, F64, dev).reshape(-1, 9)
         n_raw = int(self.cam.shape[0])
         if n_raw == 0:
@@ -84,6 +113,14 @@ class DeviceGraph:
                                      _ptr(self.raw_pair), C.byref(npairs), _ptr(ws), wsb, _stream()), "vb_ingest_sort")
             E = int(npairs.value)
             self.n_edges = E
+            if upload is not None:
+                self.marker, self.k_r, self.k_t = upload.get("marker"), upload.get("k_r"), upload.get("k_t")
+                R = upload.get("R").reshape(-1, 9)
+            else:
+                self.marker = _dev(marker, I32, dev)
+                R = _dev(R, F64, dev).reshape(-1, 9)
+                self.k_r = _dev(k_r, F64, dev)
+                self.k_t = _dev(k_t, F64, dev)
             tl = default_tile_len(E) if tile_len is None else int(tile_len)
             self.tile_len = tl
             max_tiles = int(lib.vb_ingest_max_tiles(E, self.n_c, tl))
@@ -266,12 +303,18 @@ def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int,
     With ``to_host`` the results are copied back to (pinned) host memory."""
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record()
+    upload = None
+    if graph is None and isinstance(R, torch.Tensor) and not R.is_cuda:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        upload = HostUpload(dict(cam=cam, time=time, marker=marker, k_r=k_r, k_t=k_t, R=R, t=t),
+                            dict(cam=I32, time=I32, marker=I32, k_r=F64, k_t=F64, R=F64, t=F64), dev)
     g = graph if graph is not None else DeviceGraph(cam, time, marker, R, k_r, k_t, markerC, n_c, n_t,
-                                                     round_kr_f32=round_kr_f32)
+                                                     round_kr_f32=round_kr_f32, upload=upload)
     ev[1].record()
     rot = solve_rotations(g, maxiter, tol=tol, comm=comm)
     ev[2].record()
-    tr = solve_translations(g, rot, t, marker_q, lsqr_solver, mode=mode, comm=comm)
+    tr = solve_translations(g, rot, upload.get("t") if upload is not None else t, marker_q, lsqr_solver,
+                            mode=mode, comm=comm)
     Rw_c, Rw_t = rot.world_rotations()
     x_c, x_t = tr.x_c, tr.x_t
     if to_host:
