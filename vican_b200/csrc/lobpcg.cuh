@@ -96,6 +96,9 @@ __device__ __forceinline__ void blk_times(const double* v, const double* Cm, int
 }
 
 __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParams p) {
+    // a speculatively enqueued step after convergence is a no-op (uniform across the grid: the flag
+    // was written by the previous launch)
+    if (!p.first && p.small[SM_CONV] != 0.0) return;
     cg::grid_group grid = cg::this_grid();
     __shared__ double red_sm[8 * 27];
     __shared__ double tot[LOB_NRED];

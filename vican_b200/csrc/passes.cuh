@@ -199,7 +199,10 @@ template <int MODE, int CTAS>
 __global__ void __launch_bounds__(PASS_THREADS, CTAS)
 edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ idx,
                  const double* __restrict__ B, const double* __restrict__ G, const double* __restrict__ lamT,
-                 double* __restrict__ out, int n_seg) {
+                 double* __restrict__ out, int n_seg, const double* __restrict__ skip_flag) {
+    // speculatively enqueued launches (the host polls the eigen-solver's convergence flag one
+    // iteration late) turn into no-ops once the flag is set
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;
     extern __shared__ __align__(128) unsigned char pass_smem[];
     constexpr bool TR = (MODE != 2);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -315,7 +318,9 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
 }
 
 // compact [n][9] -> padded [n][12] node blocks (the gather source layout)
-__global__ void pad_blocks_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
+__global__ void pad_blocks_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n,
+                                  const double* __restrict__ skip_flag) {
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 12 * n) return;
     const int64_t node = i / 12;
@@ -323,9 +328,9 @@ __global__ void pad_blocks_kernel(const double* __restrict__ src, double* __rest
     dst[i] = (col < 3) ? src[9 * node + 3 * row + col] : 0.0;
 }
 
-inline int launch_pad_blocks(const double* src, double* dst, int64_t n, cudaStream_t st) {
+inline int launch_pad_blocks(const double* src, double* dst, int64_t n, cudaStream_t st, const double* skip_flag = nullptr) {
     if (n <= 0) return 0;
-    pad_blocks_kernel<<<(int)((12 * n + 255) / 256), 256, 0, st>>>(src, dst, n);
+    pad_blocks_kernel<<<(int)((12 * n + 255) / 256), 256, 0, st>>>(src, dst, n, skip_flag);
     VB_KERNEL_CHECK();
     return 0;
 }
@@ -338,14 +343,14 @@ inline int pass_grid(int64_t n_segments, int ctas_per_sm) {
 
 template <int MODE>
 inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
-                            const double* lamT, double* out, int64_t n_seg, cudaStream_t st) {
+                            const double* lamT, double* out, int64_t n_seg, cudaStream_t st, const double* skip_flag) {
     constexpr int CTAS = PASS_CTAS_PER_SM;   // 5 or 6 CTAs / SM (80-96 registers) measured slower, see profiles/
     static bool attr_set = false;
     if (!attr_set) {
         VB_CHECK(cudaFuncSetAttribute(edge_pass_kernel<MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
         attr_set = true;
     }
-    edge_pass_kernel<MODE, CTAS><<<pass_grid(n_seg, CTAS), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg);
+    edge_pass_kernel<MODE, CTAS><<<pass_grid(n_seg, CTAS), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg, skip_flag);
     VB_KERNEL_CHECK();
     return 0;
 }
@@ -354,17 +359,19 @@ inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* 
 // copies are 16-byte granular); the ingestion allocates that padding.
 // X12: padded gather source [n_c][12]; out12: padded [n_t][12].
 inline int launch_pass_time(int mode, const int* rowptr, const int* cam, const double* B, const double* X12,
-                            const double* lamT, double* out12, int64_t n_t, cudaStream_t st) {
+                            const double* lamT, double* out12, int64_t n_t, cudaStream_t st,
+                            const double* skip_flag = nullptr) {
     if (n_t <= 0) return 0;
-    if (mode == 0) return launch_edge_pass<0>(rowptr, nullptr, cam, B, X12, lamT, out12, n_t, st);
-    return launch_edge_pass<1>(rowptr, nullptr, cam, B, X12, lamT, out12, n_t, st);
+    if (mode == 0) return launch_edge_pass<0>(rowptr, nullptr, cam, B, X12, lamT, out12, n_t, st, skip_flag);
+    return launch_edge_pass<1>(rowptr, nullptr, cam, B, X12, lamT, out12, n_t, st, skip_flag);
 }
 
 // tile_start carries a sentinel: tile_start[n_tiles] = E (tiles are contiguous).  W12 padded, Y compact.
 inline int launch_pass_cam(const int* tile_cam, const int* tile_start, const int* tidx, const double* B,
-                           const double* W12, double* Y, int64_t n_tiles, cudaStream_t st) {
+                           const double* W12, double* Y, int64_t n_tiles, cudaStream_t st,
+                           const double* skip_flag = nullptr) {
     if (n_tiles <= 0) return 0;
-    return launch_edge_pass<2>(tile_start, tile_cam, tidx, B, W12, nullptr, Y, n_tiles, st);
+    return launch_edge_pass<2>(tile_start, tile_cam, tidx, B, W12, nullptr, Y, n_tiles, st, skip_flag);
 }
 
 }  // namespace vb

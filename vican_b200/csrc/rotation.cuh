@@ -149,14 +149,20 @@ inline So3Work carve_so3(void* base, int64_t n_c, int64_t n_t) {
     return w;
 }
 
+constexpr int STATUS_SLOTS = 4;
 struct PinnedStatus {
     double* h = nullptr;
-    PinnedStatus() { cudaMallocHost((void**)&h, SM_SIZE * sizeof(double)); }
+    cudaEvent_t ev[STATUS_SLOTS];
+    PinnedStatus() {
+        cudaMallocHost((void**)&h, STATUS_SLOTS * SM_SIZE * sizeof(double));
+        for (int i = 0; i < STATUS_SLOTS; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    }
 };
-inline double* pinned_status() {
+inline PinnedStatus& pinned_state() {
     static thread_local PinnedStatus s;
-    return s.h;
+    return s;
 }
+inline double* pinned_status() { return pinned_state().h; }
 
 inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, double* r_t, void* workspace,
                        int64_t workspace_bytes, vb_so3_stats* stats, cudaStream_t st) {
@@ -171,16 +177,16 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     const size_t cbytes = 9 * n_c * sizeof(double);
     int status = VB_STATUS_OK;
 
-    auto time_pass = [&](int mode, const double* X, double* out) -> int {
+    auto time_pass = [&](int mode, const double* X, double* out, const double* skip = nullptr) -> int {
         S->time_passes++; S->kernel_launches += 2;
-        int rc = launch_pad_blocks(X, w.Xpad, n_c, st);   // gather source layout: 3 rows x 4 doubles
+        int rc = launch_pad_blocks(X, w.Xpad, n_c, st, skip);   // gather source layout: 3 rows x 4 doubles
         if (rc) return rc;
-        return launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, w.Xpad, w.lamT, out, n_t, st);
+        return launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, w.Xpad, w.lamT, out, n_t, st, skip);
     };
-    auto cam_pass = [&](const double* Wt, double* Y) -> int {
+    auto cam_pass = [&](const double* Wt, double* Y, const double* skip = nullptr) -> int {
         VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
         S->cam_passes++; S->kernel_launches++;
-        int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, Wt, Y, g->n_tiles, st);
+        int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, Wt, Y, g->n_tiles, st, skip);
         if (rc) return rc;
         if (opt->allreduce) return opt->allreduce(opt->allreduce_ctx, Y, 9 * n_c, (void*)st);
         return 0;
@@ -214,23 +220,52 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         lp.first = 1;
         VB_RC(launch_lobpcg_step(lp, st));
         S->lobpcg_steps++; S->kernel_launches++;
-        int inner = 1;
+        // The host polls the convergence flag ONE step late: step k+1 (edge passes + LOBPCG kernel)
+        // is enqueued before the status of step k is read, so the GPU never idles on the host.  Once
+        // the flag is set on the device the speculative launches return immediately.
+        PinnedStatus& ps = pinned_state();
+        const double* conv_flag = w.small + SM_CONV;
+        auto readback = [&](int step) -> int {
+            const int slot = step % STATUS_SLOTS;
+            VB_CHECK(cudaMemcpyAsync(ps.h + slot * SM_SIZE, w.small, SM_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+            VB_CHECK(cudaEventRecord(ps.ev[slot], st));
+            return 0;
+        };
+        VB_RC(readback(1));
+        int inner = 1;            // steps whose work was (or will be) really executed
+        int enqueued = 1;         // steps enqueued so far
         double hist[3] = {1e300, 1e300, 1e300};   // residuals of the last three steps (stagnation guard)
         for (;;) {
-            VB_CHECK(cudaMemcpyAsync(hs, w.small, SM_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
-            VB_CHECK(cudaStreamSynchronize(st));
-            if (hs[SM_CONV] != 0.0) break;
-            // rounding floor reached: the residual stopped shrinking although it is already tiny
+            bool speculated = false;
+            if (enqueued < max_inner) {
+                VB_RC(time_pass(0, w.W, w.Wt, conv_flag));
+                VB_RC(cam_pass(w.Wt, w.Y, conv_flag));
+                lp.first = 0;
+                VB_RC(launch_lobpcg_step(lp, st));
+                S->lobpcg_steps++; S->kernel_launches++;
+                ++enqueued;
+                VB_RC(readback(enqueued));
+                speculated = true;
+            }
+            const int slot = inner % STATUS_SLOTS;
+            VB_CHECK(cudaEventSynchronize(ps.ev[slot]));
+            hs = ps.h + slot * SM_SIZE;
+            if (hs[SM_CONV] != 0.0) {
+                if (speculated) { S->time_passes--; S->cam_passes--; S->lobpcg_steps--; S->kernel_launches -= 4; }
+                break;
+            }
+            if (!speculated) { S->stalled_outer++; status = VB_STATUS_EIG_STALLED; break; }
+            // rounding floor reached: the residual stopped shrinking although it is already tiny.  The
+            // step enqueued above still runs (its flag test sees "not converged"); take its iterate.
             const double rmax = fmax(hs[SM_RESN], fmax(hs[SM_RESN + 1], hs[SM_RESN + 2]));
-            if (rmax < 1e-9 * hs[SM_ANORM] && rmax > 0.5 * hist[0]) break;
+            const bool floor_hit = (rmax < 1e-9 * hs[SM_ANORM] && rmax > 0.5 * hist[0]);
             hist[0] = hist[1]; hist[1] = hist[2]; hist[2] = rmax;
-            if (inner >= max_inner) { S->stalled_outer++; status = VB_STATUS_EIG_STALLED; break; }
-            VB_RC(time_pass(0, w.W, w.Wt));
-            VB_RC(cam_pass(w.Wt, w.Y));
-            lp.first = 0;
-            VB_RC(launch_lobpcg_step(lp, st));
-            S->lobpcg_steps++; S->kernel_launches++;
             ++inner;
+            if (floor_hit) {
+                VB_CHECK(cudaEventSynchronize(ps.ev[inner % STATUS_SLOTS]));
+                hs = ps.h + (inner % STATUS_SLOTS) * SM_SIZE;
+                break;
+            }
         }
         if (outer < 64) S->inner_per_outer[outer] = inner;
         for (int j = 0; j < 3; ++j) { S->theta[j] = hs[SM_THETA + j]; S->resid[j] = hs[SM_RESN + j]; }
