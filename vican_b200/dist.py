@@ -29,8 +29,12 @@ def init_process_group_from_env(backend: Optional[str] = None):
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world
 
 
