@@ -89,10 +89,15 @@ def test_se3_batch_kernels_vs_container(cuda):
     assert np.abs(ti64.cpu().numpy() + np.einsum("nji,nj->ni", Ra, ta)).max() < 1e-14
 
 
+@pytest.mark.parametrize("shuffle", [False, True])
 @pytest.mark.parametrize("shape", [(12, 80, 4, 4, 2), (20, 300, 6, 7, 3), (40, 500, 24, 20, 10), (7, 50, 3, 7, 3)])
-def test_ingestion_matches_oracle_aggregation(cuda, shape):
+def test_ingestion_matches_oracle_aggregation(cuda, shape, shuffle):
     g = syn.make_camera_network(3, *shape, outlier_frac=0.1)
     a = _arrays(g)
+    if shuffle:   # detections in arbitrary order: exercises the radix-sort path (sorted input skips it)
+        perm = np.random.default_rng(0).permutation(a["cam"].shape[0])
+        for k in ("cam", "time", "marker", "R", "t", "k_r", "k_t"):
+            a[k] = np.ascontiguousarray(a[k][perm])
     dg = _device_graph(g, a)
     pc, pt, B, av = _oracle_pairs(g, a)
     assert dg.n_edges == pc.shape[0]

@@ -52,6 +52,8 @@ __global__ void pair_start_kernel(const int* __restrict__ raw_pair, int* __restr
 }
 
 // One thread per aggregated pair: fold the constraint and sum in original detection order.
+// (A 9-threads-per-pair variant with coalesced 72-byte accesses was measured SLOWER: the index
+// loads are repeated by every thread and dominate when pairs hold one or two detections.)
 __global__ void fold_aggregate_kernel(const int* __restrict__ cam, const int* __restrict__ time, const int* __restrict__ marker,
                                       const double* __restrict__ R, const double* __restrict__ k_r, const double* __restrict__ k_t,
                                       const double* __restrict__ markerC, int round_f32, const int* __restrict__ raw_perm,
@@ -85,6 +87,16 @@ __global__ void fold_aggregate_kernel(const int* __restrict__ cam, const int* __
     for (int i = 0; i < 9; ++i) t_B[9 * p + i] = B[i];
     t_a[p] = a;
     t_w[p] = w;
+}
+
+__global__ void check_sorted_kernel(const uint64_t* __restrict__ keys, int64_t n, int* __restrict__ unsorted_flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && keys[i] > keys[i + 1]) *unsorted_flag = 1;
+}
+
+__global__ void iota_kernel(int* __restrict__ v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int)i;
 }
 
 // ptr[v] = first position whose (sorted) node id is >= v, for v in [0, n_nodes]
@@ -229,10 +241,23 @@ inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     make_keys_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(time, cam, n_c, w.keys_a, w.vals_a, n_raw);
     VB_KERNEL_CHECK();
+    // adaptive: detections that already arrive ordered by (time, camera) -- the usual layout of a
+    // recording -- skip the radix sort (one 8-byte pass instead of five 24-byte passes)
+    VB_CHECK(cudaMemsetAsync(w.tmp_a, 0, sizeof(int), st));
+    check_sorted_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(w.keys_a, n_raw, w.tmp_a);
+    int unsorted = 0;
+    VB_CHECK(cudaMemcpyAsync(&unsorted, w.tmp_a, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VB_CHECK(cudaStreamSynchronize(st));
     size_t tb = w.cub_bytes;
-    VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
-                                             raw_perm, (int)n_raw, 0, key_bits(n_c, n_t), st));
-    head_flags_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(w.keys_b, w.tmp_a, n_raw);
+    const uint64_t* keys_sorted = w.keys_a;
+    if (unsorted) {
+        VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
+                                                 raw_perm, (int)n_raw, 0, key_bits(n_c, n_t), st));
+        keys_sorted = w.keys_b;
+    } else {
+        iota_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(raw_perm, n_raw);
+    }
+    head_flags_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(keys_sorted, w.tmp_a, n_raw);
     VB_KERNEL_CHECK();
     tb = w.cub_bytes;
     VB_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, (const int*)w.tmp_a, w.tmp_b, (int)n_raw, st));

@@ -196,8 +196,9 @@ __global__ void cg_dir_kernel(const double* __restrict__ r, const double* __rest
 }
 
 // time side of q = (J^T J) p : warp per time node (persistent, grid-stride); also accumulates p_t . q_t.
-// Two edges per lane are loaded back to back (degree <= 64 needs a single round trip) and the row
-// pointers of the warp's next node are fetched while the current one is reduced.
+// Software pipelined: the indices / weights of the warp's NEXT node (two edges per lane, i.e. up to 64
+// edges) and the row pointers of the one after are in flight while the current node's rows are gathered
+// and reduced, so the only exposed latency per node is the (L2-resident) gather.
 // The product is evaluated as  dg_t p_t - sum w p_c  (diagonal term separate, like the explicit CSR
 // product of J^T J that scipy's cg multiplies with): measured on the object-calibration graphs, the
 // truncated CG iterate is ~8x less sensitive to this rounding pattern than to sum w (p_t - p_c).
@@ -210,25 +211,38 @@ cg_time_kernel(const int* __restrict__ rowptr, const int* __restrict__ cam, cons
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double dot[1] = {0.0};
-    int s = 0, e = 0;
+    auto load_head = [&](int s, int e, int& ca, int& cb, double& wa, double& wb) {
+        const int i = s + lane, i2 = i + 32;
+        ca = 0; cb = 0; wa = 0.0; wb = 0.0;
+        if (i < e) { ca = cam[i]; wa = w[i]; }
+        if (i2 < e) { cb = cam[i2]; wb = w[i2]; }
+    };
+    int s = 0, e = 0, s2 = 0, e2 = 0;
     if (warp0 < n_t) { s = __ldg(rowptr + warp0); e = __ldg(rowptr + warp0 + 1); }
+    if (warp0 + nwarps < n_t) { s2 = __ldg(rowptr + warp0 + nwarps); e2 = __ldg(rowptr + warp0 + nwarps + 1); }
+    int ca, cb; double wa, wb;
+    load_head(s, e, ca, cb, wa, wb);
     for (int64_t node = warp0; node < n_t; node += nwarps) {
-        const int64_t nxt = node + nwarps;
-        int s2 = 0, e2 = 0;
-        if (nxt < n_t) { s2 = __ldg(rowptr + nxt); e2 = __ldg(rowptr + nxt + 1); }
+        // prefetch: head of the next node, row pointers of the one after
+        int nca, ncb; double nwa, nwb;
+        load_head(s2, e2, nca, ncb, nwa, nwb);
+        const int64_t n3 = node + 2 * nwarps;
+        int s3 = 0, e3 = 0;
+        if (n3 < n_t) { s3 = __ldg(rowptr + n3); e3 = __ldg(rowptr + n3 + 1); }
         const double x0 = p_t[4 * node], x1 = p_t[4 * node + 1], x2 = p_t[4 * node + 2];
         double a0 = 0, a1 = 0, a2 = 0;
-        for (int i = s + lane; i < e; i += 64) {
-            const int i2 = i + 32;
-            const bool two = i2 < e;
-            const int64_t ca = cam[i], cb = two ? cam[i2] : 0;
-            const double wa = w[i], wb = two ? w[i2] : 0.0;
-            double g0, g1, g2, h0 = 0.0, h1 = 0.0, h2 = 0.0;
-            ld_row256(p_c + 4 * ca, g0, g1, g2);
-            if (two) ld_row256(p_c + 4 * cb, h0, h1, h2);
-            a0 += wa * g0 + wb * h0;
-            a1 += wa * g1 + wb * h1;
-            a2 += wa * g2 + wb * h2;
+        {   // first 64 edges: indices / weights already in registers
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, h0 = 0.0, h1 = 0.0, h2 = 0.0;
+            if (s + lane < e) ld_row256(p_c + 4 * (int64_t)ca, g0, g1, g2);
+            if (s + lane + 32 < e) ld_row256(p_c + 4 * (int64_t)cb, h0, h1, h2);
+            a0 = wa * g0 + wb * h0; a1 = wa * g1 + wb * h1; a2 = wa * g2 + wb * h2;
+        }
+        for (int i = s + 64 + lane; i < e; i += 32) {   // high-degree tail
+            const int64_t c = cam[i];
+            const double ww = w[i];
+            double g0, g1, g2;
+            ld_row256(p_c + 4 * c, g0, g1, g2);
+            a0 += ww * g0; a1 += ww * g1; a2 += ww * g2;
         }
         a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
         if (lane == 0) {
@@ -237,13 +251,15 @@ cg_time_kernel(const int* __restrict__ rowptr, const int* __restrict__ cam, cons
             q_t[3 * node] = a0; q_t[3 * node + 1] = a1; q_t[3 * node + 2] = a2;
             dot[0] += x0 * a0 + x1 * a1 + x2 * a2;
         }
-        s = s2; e = e2;
+        s = s2; e = e2; s2 = s3; e2 = e3;
+        ca = nca; cb = ncb; wa = nwa; wb = nwb;
     }
     double* const dst[1] = {sc + CG_PQ_T};
     block_atomic_sum<1>(dot, dst);
 }
 
-// camera side: warp per camera tile, 3 atomics per tile (q_c zeroed before)
+// camera side: warp per camera tile, accumulates -sum w p_t with 3 atomics per tile (q_c holds dg_c p_c);
+// the indices / weights of the next 64-edge chunk are loaded before the current chunk's rows are gathered
 __global__ void cg_cam_kernel(const int* __restrict__ tile_cam, const int* __restrict__ tile_start, const int* __restrict__ tile_end,
                               const int* __restrict__ tidx, const double* __restrict__ w, const double* __restrict__ p_c,
                               const double* __restrict__ p_t, double* __restrict__ q_c, int64_t n_tiles, const double* sc) {
@@ -252,19 +268,26 @@ __global__ void cg_cam_kernel(const int* __restrict__ tile_cam, const int* __res
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= n_tiles) return;
     const int64_t c = tile_cam[warp];
+    const int ts = tile_start[warp], te = tile_end[warp];
+    auto load_chunk = [&](int base, int& ta, int& tb, double& wa, double& wb) {
+        const int i = base + lane, i2 = i + 32;
+        ta = 0; tb = 0; wa = 0.0; wb = 0.0;
+        if (i < te) { ta = tidx[i]; wa = w[i]; }
+        if (i2 < te) { tb = tidx[i2]; wb = w[i2]; }
+    };
     double a0 = 0, a1 = 0, a2 = 0;
-    const int te = tile_end[warp];
-    for (int i = tile_start[warp] + lane; i < te; i += 64) {
-        const int i2 = i + 32;
-        const bool two = i2 < te;
-        const int64_t ta = tidx[i], tb = two ? tidx[i2] : 0;
-        const double wa = w[i], wb = two ? w[i2] : 0.0;
-        double g0, g1, g2, h0 = 0.0, h1 = 0.0, h2 = 0.0;
-        ld_row256(p_t + 4 * ta, g0, g1, g2);
-        if (two) ld_row256(p_t + 4 * tb, h0, h1, h2);
+    int ta, tb; double wa, wb;
+    load_chunk(ts, ta, tb, wa, wb);
+    for (int base = ts; base < te; base += 64) {
+        int nta, ntb; double nwa, nwb;
+        load_chunk(base + 64, nta, ntb, nwa, nwb);
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0, h0 = 0.0, h1 = 0.0, h2 = 0.0;
+        if (base + lane < te) ld_row256(p_t + 4 * (int64_t)ta, g0, g1, g2);
+        if (base + lane + 32 < te) ld_row256(p_t + 4 * (int64_t)tb, h0, h1, h2);
         a0 -= wa * g0 + wb * h0;
         a1 -= wa * g1 + wb * h1;
         a2 -= wa * g2 + wb * h2;
+        ta = nta; tb = ntb; wa = nwa; wb = nwb;
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { atomicAdd(q_c + 3 * c, a0); atomicAdd(q_c + 3 * c + 1, a1); atomicAdd(q_c + 3 * c + 2, a2); }

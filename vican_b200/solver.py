@@ -52,16 +52,25 @@ class HostUpload:
         self.stream = torch.cuda.Stream(device=device)
         self._t, self._ev = {}, {}
         cur = torch.cuda.current_stream(device)
+        # destinations are allocated on the COMPUTE stream (no cross-stream traffic in the caching
+        # allocator: allocating them on the side stream made it fall back to cudaMalloc / cudaFree)
+        dst = {}
+        for name in self.ORDER:
+            if name in arrays:
+                src = arrays[name]
+                src = src if isinstance(src, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(src))
+                arrays[name] = src.contiguous()
+                dst[name] = torch.empty(src.shape, dtype=dtypes[name], device=device)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             for name in self.ORDER:
-                if name not in arrays:
+                if name not in dst:
                     continue
-                t = _dev(arrays[name], dtypes[name], device)
-                t.record_stream(cur)
+                dst[name].copy_(arrays[name], non_blocking=True)
+                dst[name].record_stream(self.stream)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
-                self._t[name], self._ev[name] = t, ev
+                self._t[name], self._ev[name] = dst[name], ev
 
     def get(self, name):
         torch.cuda.current_stream(self.device).wait_event(self._ev[name])
@@ -280,6 +289,21 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
     return TranslationResult(x_c, x_t, int(iters.value), int(istop.value))
 
 
+_PINNED_OUT = {}
+
+
+def _to_pinned_host(name: str, t: torch.Tensor) -> torch.Tensor:
+    """Device -> host copy into a cached PINNED buffer (pageable destinations run at a few GB/s).
+    The buffer is reused by the next call with the same name and shape."""
+    key = (name, tuple(t.shape), t.dtype)
+    buf = _PINNED_OUT.get(key)
+    if buf is None:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        _PINNED_OUT[key] = buf
+    buf.copy_(t, non_blocking=True)
+    return buf
+
+
 @dataclasses.dataclass
 class SolveResult:
     Rw_c: torch.Tensor          # [n_c, 3, 3] world rotations of the cameras
@@ -318,7 +342,8 @@ def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int,
     Rw_c, Rw_t = rot.world_rotations()
     x_c, x_t = tr.x_c, tr.x_t
     if to_host:
-        Rw_c, Rw_t, x_c, x_t = (v.to("cpu", non_blocking=False) for v in (Rw_c, Rw_t, x_c, x_t))
+        Rw_c, Rw_t, x_c, x_t = (_to_pinned_host(n, v) for n, v in
+                                (("Rw_c", Rw_c), ("Rw_t", Rw_t), ("x_c", x_c), ("x_t", x_t)))
     ev[3].record()
     torch.cuda.synchronize()
     phase = dict(ingest=ev[0].elapsed_time(ev[1]), rotation=ev[1].elapsed_time(ev[2]),
