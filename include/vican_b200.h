@@ -63,6 +63,8 @@ typedef struct vb_so3_options {
     double  tol;            /* eigen-residual tolerance relative to rms(Lambda_C) */
     vb_allreduce_fn allreduce;
     void*   allreduce_ctx;
+    int32_t profile_events; /* != 0: bracket every edge-pass launch with CUDA events (stats->*_pass_ms) */
+    int32_t reserved;
 } vb_so3_options;
 
 typedef struct vb_so3_stats {
@@ -76,6 +78,12 @@ typedef struct vb_so3_stats {
     double  resid[3];       /* last eigen-residual norms */
     double  anorm;
     int32_t inner_per_outer[64];
+    /* filled when opt->profile_events: device time of the EXECUTED edge passes (speculative launches
+     * that were skipped on the device are excluded), measured with CUDA events on the solver's stream */
+    double  time_pass_ms;   /* sum over executed time passes (modes 0 and 1) */
+    double  cam_pass_ms;    /* sum over executed camera passes */
+    int32_t time_pass_timed;
+    int32_t cam_pass_timed;
 } vb_so3_stats;
 
 const char* vb_version(void);

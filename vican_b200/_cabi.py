@@ -39,7 +39,8 @@ class VbGraph(C.Structure):
 
 
 class VbSo3Options(C.Structure):
-    _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP)]
+    _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP),
+                ("profile_events", I32), ("reserved", I32)]
 
 
 class VbSo3Stats(C.Structure):
@@ -47,6 +48,7 @@ class VbSo3Stats(C.Structure):
         ("outer_done", I32), ("time_passes", I32), ("cam_passes", I32), ("lobpcg_steps", I32),
         ("kernel_launches", I32), ("stalled_outer", I32),
         ("theta", F64 * 3), ("resid", F64 * 3), ("anorm", F64), ("inner_per_outer", I32 * 64),
+        ("time_pass_ms", F64), ("cam_pass_ms", F64), ("time_pass_timed", I32), ("cam_pass_timed", I32),
     ]
 
 

@@ -150,12 +150,20 @@ inline So3Work carve_so3(void* base, int64_t n_c, int64_t n_t) {
 }
 
 constexpr int STATUS_SLOTS = 4;
+constexpr int PROF_EVENTS = 1024;   // begin/end pairs for up to 512 edge-pass launches per run
 struct PinnedStatus {
     double* h = nullptr;
     cudaEvent_t ev[STATUS_SLOTS];
+    cudaEvent_t prof[PROF_EVENTS];
+    bool prof_ready = false;
     PinnedStatus() {
         cudaMallocHost((void**)&h, STATUS_SLOTS * SM_SIZE * sizeof(double));
         for (int i = 0; i < STATUS_SLOTS; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    }
+    void ensure_prof() {
+        if (prof_ready) return;
+        for (int i = 0; i < PROF_EVENTS; ++i) cudaEventCreate(&prof[i]);
+        prof_ready = true;
     }
 };
 inline PinnedStatus& pinned_state() {
@@ -177,16 +185,40 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     const size_t cbytes = 9 * n_c * sizeof(double);
     int status = VB_STATUS_OK;
 
+    // optional per-launch CUDA-event timing of the edge passes (bench.py's in-step roofline)
+    PinnedStatus& pst = pinned_state();
+    const bool prof = opt->profile_events != 0;
+    if (prof) pst.ensure_prof();
+    int n_prof = 0;                 // events used so far
+    signed char prof_kind[PROF_EVENTS / 2];   // 0 = time pass, 1 = camera pass, -1 = skipped on the device
+    int last_time_slot = -1, last_cam_slot = -1;
+    auto prof_begin = [&](int kind) -> int {
+        if (!prof || n_prof + 2 > PROF_EVENTS) return -1;
+        const int slot = n_prof / 2;
+        prof_kind[slot] = (signed char)kind;
+        cudaEventRecord(pst.prof[n_prof], st);
+        n_prof += 2;
+        return slot;
+    };
+    auto prof_end = [&](int slot) { if (slot >= 0) cudaEventRecord(pst.prof[2 * slot + 1], st); };
+
     auto time_pass = [&](int mode, const double* X, double* out, const double* skip = nullptr) -> int {
         S->time_passes++; S->kernel_launches += 2;
         int rc = launch_pad_blocks(X, w.Xpad, n_c, st, skip);   // gather source layout: 3 rows x 4 doubles
         if (rc) return rc;
-        return launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, w.Xpad, w.lamT, out, n_t, st, skip);
+        const int slot = prof_begin(0);
+        rc = launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, w.Xpad, w.lamT, out, n_t, st, skip);
+        prof_end(slot);
+        last_time_slot = slot;
+        return rc;
     };
     auto cam_pass = [&](const double* Wt, double* Y, const double* skip = nullptr) -> int {
         VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
         S->cam_passes++; S->kernel_launches++;
+        const int slot = prof_begin(1);
         int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, Wt, Y, g->n_tiles, st, skip);
+        prof_end(slot);
+        last_cam_slot = slot;
         if (rc) return rc;
         if (opt->allreduce) return opt->allreduce(opt->allreduce_ctx, Y, 9 * n_c, (void*)st);
         return 0;
@@ -251,7 +283,11 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
             VB_CHECK(cudaEventSynchronize(ps.ev[slot]));
             hs = ps.h + slot * SM_SIZE;
             if (hs[SM_CONV] != 0.0) {
-                if (speculated) { S->time_passes--; S->cam_passes--; S->lobpcg_steps--; S->kernel_launches -= 4; }
+                if (speculated) {
+                    S->time_passes--; S->cam_passes--; S->lobpcg_steps--; S->kernel_launches -= 4;
+                    if (last_time_slot >= 0) prof_kind[last_time_slot] = -1;
+                    if (last_cam_slot >= 0) prof_kind[last_cam_slot] = -1;
+                }
                 break;
             }
             if (!speculated) { S->stalled_outer++; status = VB_STATUS_EIG_STALLED; break; }
@@ -285,6 +321,15 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         S->outer_done = outer + 1;
     }
     VB_CHECK(cudaStreamSynchronize(st));
+    if (prof) {
+        for (int slot = 0; slot < n_prof / 2; ++slot) {
+            if (prof_kind[slot] < 0) continue;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pst.prof[2 * slot], pst.prof[2 * slot + 1]) != cudaSuccess) continue;
+            if (prof_kind[slot] == 0) { S->time_pass_ms += ms; S->time_pass_timed++; }
+            else { S->cam_pass_ms += ms; S->cam_pass_timed++; }
+        }
+    }
     return status;
 #undef VB_RC
 }

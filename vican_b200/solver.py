@@ -194,7 +194,7 @@ class RotationResult:
 
 
 def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner: int = 200,
-                    comm: Optional[Comm] = None) -> RotationResult:
+                    comm: Optional[Comm] = None, profile_events: bool = False) -> RotationResult:
     lib = _cabi.lib()
     dev = g.device
     with torch.cuda.device(dev):
@@ -204,7 +204,7 @@ def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner:
         r_t = torch.empty((g.n_t, 9), dtype=F64, device=dev)
         opt = VbSo3Options(int(maxiter), int(max_inner), float(tol),
                            lib.vb_nccl_allreduce_fn() if comm is not None else None,
-                           comm.ctx if comm is not None else None)
+                           comm.ctx if comm is not None else None, 1 if profile_events else 0, 0)
         stats = VbSo3Stats()
         rc = lib.vb_so3sync_run(C.byref(g.cgraph), C.byref(opt), _ptr(r_c), _ptr(r_t), _ptr(ws), wsb,
                                 C.byref(stats), _stream())
@@ -319,7 +319,7 @@ class SolveResult:
 def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int, n_t: int, maxiter: int,
                  lsqr_solver: str = "conjugate_gradient", mode: str = "parity", tol: float = 1e-13,
                  comm: Optional[Comm] = None, round_kr_f32: bool = False, to_host: bool = False,
-                 graph: Optional[DeviceGraph] = None) -> SolveResult:
+                 graph: Optional[DeviceGraph] = None, profile_events: bool = False) -> SolveResult:
     """Array fast path of ``bipartite_se3sync`` (no dicts, no Python callables): raw detections
     as arrays (numpy / pinned host tensors / CUDA tensors) with pre-evaluated weights
     ``k_r = noise_model_r(e)``, ``k_t = noise_model_t(e)`` and already filtered by
@@ -335,7 +335,7 @@ def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int,
     g = graph if graph is not None else DeviceGraph(cam, time, marker, R, k_r, k_t, markerC, n_c, n_t,
                                                      round_kr_f32=round_kr_f32, upload=upload)
     ev[1].record()
-    rot = solve_rotations(g, maxiter, tol=tol, comm=comm)
+    rot = solve_rotations(g, maxiter, tol=tol, comm=comm, profile_events=profile_events)
     ev[2].record()
     tr = solve_translations(g, rot, upload.get("t") if upload is not None else t, marker_q, lsqr_solver,
                             mode=mode, comm=comm)
