@@ -1,0 +1,169 @@
+"""Host side of the ingestion: dictionary flatten, pre-evaluated array
+path, streaming accumulator, reader of the notebook's ``cam_marker_edges.pt``.  CPU only."""
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from vican_b200 import io as vio
+from vican_b200 import synthetic as syn
+from vican_b200.bipgo import EdgeTable
+from vican_b200.geometry import SE3
+
+FIELDS = ("cam_ids", "time_ids", "marker_ids", "cam_idx", "time_idx", "marker_idx", "R", "t", "k_r", "k_t",
+          "markerC", "marker_q", "round_kr_f32", "root", "n_raw")
+
+
+def _graph(outliers=0.2):
+    return syn.make_camera_network(3, 12, 40, 4, 5, 2, outlier_frac=outliers)
+
+
+def _same(a, b):
+    for f in FIELDS:
+        x, y = np.asarray(getattr(a, f)), np.asarray(getattr(b, f))
+        assert x.dtype == y.dtype and np.array_equal(x, y), f
+
+
+def test_node_order_is_the_references_lexicographic_order():
+    """bipgo.py:225-229: nodes = np.unique(strings) -> '10' sorts before '2'."""
+    g = _graph(0.0)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    tab = EdgeTable(edges, cons, nr, nt, ef)
+    assert list(tab.cam_ids) == sorted({k[0] for k in edges})
+    assert list(tab.time_ids) == sorted({k[1].split("_")[0] for k in edges})
+    assert list(tab.cam_ids).index("10") < list(tab.cam_ids).index("2")
+    # every detection is coded with the index of its own ids
+    keys = list(edges.keys())
+    for e in (0, len(keys) // 2, len(keys) - 1):
+        assert tab.cam_ids[tab.cam_idx[e]] == keys[e][0]
+        assert tab.time_ids[tab.time_idx[e]] == keys[e][1].split("_")[0]
+        assert tab.marker_ids[tab.marker_idx[e]] == keys[e][1].split("_")[1]
+        assert np.array_equal(tab.R[e].reshape(3, 3), edges[keys[e]]["pose"].R())
+
+
+def test_callables_see_only_kept_detections_and_once():
+    g = _graph(0.3)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    calls = {"f": 0, "r": 0, "t": 0}
+
+    def ef(e):
+        calls["f"] += 1
+        return e["reprojected_err"] < 0.5
+
+    def nr(e):
+        assert e["reprojected_err"] < 0.5
+        calls["r"] += 1
+        return e["w"]
+
+    def nt(e):
+        assert e["reprojected_err"] < 0.5
+        calls["t"] += 1
+        return 2.0 * e["w"]
+
+    tab = EdgeTable(edges, cons, nr, nt, ef)
+    assert calls["f"] == len(edges) and calls["r"] == tab.n_raw and calls["t"] == tab.n_raw
+    assert 0 < tab.n_raw < len(edges)
+
+
+def test_missing_constraint_is_a_keyerror_and_empty_is_a_valueerror():
+    g = _graph(0.0)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    bad = dict(cons)
+    del bad[sorted(bad)[-1]]
+    with pytest.raises(KeyError):
+        EdgeTable(edges, bad, nr, nt, ef)
+    with pytest.raises(ValueError):
+        EdgeTable(edges, cons, nr, nt, lambda e: False)
+
+
+def test_from_arrays_equals_dict_flatten():
+    g = _graph(0.2)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    tab = EdgeTable(edges, cons, nr, nt, ef)
+    kept = [(k, v) for k, v in edges.items() if ef(v)]
+    tab2 = EdgeTable.from_arrays([k[0] for k, _ in kept], [k[1] for k, _ in kept],
+                                 np.stack([v["pose"].R() for _, v in kept]), np.stack([v["pose"].t() for _, v in kept]),
+                                 np.array([nr(v) for _, v in kept]), np.array([nt(v) for _, v in kept]), cons)
+    for f in FIELDS:
+        if f == "round_kr_f32":
+            continue
+        x, y = np.asarray(getattr(tab, f)), np.asarray(getattr(tab2, f))
+        assert np.array_equal(x, y), f
+
+
+def test_accumulator_streams_per_image_chunks():
+    g = _graph(0.2)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    tab = EdgeTable(edges, cons, nr, nt, ef)
+    acc = vio.EdgeAccumulator(nr, nt, ef)
+    # chunks = detections of one image (one camera at one timestep), as estimate_pose_worker returns them
+    chunks = {}
+    for k, v in edges.items():
+        chunks.setdefault(v["im_filename"], {})[k] = v
+    assert acc.add(None) == 0                       # images without detections yield None (cam.py:139)
+    n = sum(acc.add(c) for c in chunks.values())
+    assert n == tab.n_raw == len(acc)
+    tab2 = acc.table(cons)
+    # same multiset of detections; the order follows arrival, so compare through a canonical sort
+    def canon(t):
+        key = np.lexsort((t.marker_idx, t.cam_idx, t.time_idx))
+        return t.cam_idx[key], t.time_idx[key], t.marker_idx[key], t.R[key], t.t[key], t.k_r[key], t.k_t[key]
+    for x, y in zip(canon(tab), canon(tab2)):
+        assert np.array_equal(x, y)
+    # a re-detected key replaces the older detection instead of duplicating it
+    k0 = next(k for k, v in edges.items() if ef(v))
+    assert acc.add({k0: edges[k0]}) == 1 and len(acc) == tab.n_raw
+
+
+def test_marker_whitelist_like_estimate_pose_mp():
+    g = _graph(0.0)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    acc = vio.EdgeAccumulator(nr, nt, ef, marker_ids=["0", "1"])
+    acc.add(edges)
+    assert len(acc) == sum(1 for k in edges if k[1].split("_")[1] in ("0", "1"))
+
+
+def test_load_edges_reads_reference_pickles_without_the_reference_package(tmp_path):
+    """main.ipynb cell 3/5: torch.save(dict with vican.geometry.SE3 values).  The loader maps that
+    class onto ours, so /root/reference need not be importable."""
+    import torch
+
+    # a stand-in with the reference container's attribute layout (geometry.py:194-218)
+    pkg, mod = types.ModuleType("vican"), types.ModuleType("vican.geometry")
+
+    class RefSE3(object):
+        def __init__(self, R, t):
+            self._R, self._t = R, t
+            self._pose = np.eye(4, dtype=np.float32)
+            self._pose[:3, :3] = R
+            self._pose[:3, 3] = t
+
+    RefSE3.__name__ = RefSE3.__qualname__ = "SE3"
+    RefSE3.__module__ = "vican.geometry"
+    mod.SE3 = RefSE3
+    pkg.geometry = mod
+    sys.modules["vican"], sys.modules["vican.geometry"] = pkg, mod
+    try:
+        g = _graph(0.0)
+        src = {}
+        for e in range(20):
+            src[(str(g.cam[e]), "%d_%d" % (g.time[e], g.marker[e]))] = {
+                "pose": RefSE3(g.R[e].copy(), g.t[e].copy()), "corners": np.zeros((4, 2)),
+                "reprojected_err": 0.01, "im_filename": "x"}
+        path = str(tmp_path / "cam_marker_edges.pt")
+        torch.save(src, path)
+    finally:
+        del sys.modules["vican"], sys.modules["vican.geometry"]
+    out = vio.load_edges(path)
+    assert list(out.keys()) == list(src.keys())
+    for k in src:
+        assert type(out[k]["pose"]) is SE3
+        assert np.array_equal(out[k]["pose"].R(), src[k]["pose"]._R)
+        assert np.array_equal(out[k]["pose"].t(), src[k]["pose"]._t)
+        assert np.allclose(out[k]["pose"].inv().R(), src[k]["pose"]._R.T, atol=1e-6)

@@ -41,6 +41,16 @@ class SE3:
             m[-1, -1] += 1.0
             self._pose = m
 
+    def __getstate__(self):
+        return {"_pose": self._pose, "_R": self._R, "_t": self._t}
+
+    def __setstate__(self, state):
+        # also accepts the attribute dictionary of a pickled reference SE3 (cam_marker_edges.pt)
+        if isinstance(state, tuple):
+            state = {**(state[0] or {}), **(state[1] or {})}
+        for k in ("_pose", "_R", "_t"):
+            object.__setattr__(self, k, state[k])
+
     def R(self) -> np.ndarray:
         return self._R
 

@@ -1,0 +1,114 @@
+"""Data formats either side of the solver.
+
+* ``load_edges``: reads the ``cam_marker_edges.pt`` files written by the reference's notebook
+  (``torch.save(estimate_pose_mp(...))``, main.ipynb cells 3 and 5).  They are pickles of
+  ``{(camera_id, "<timestamp>_<marker_id>"): {'pose': vican.geometry.SE3, 'corners': ...,
+  'reprojected_err': ..., 'im_filename': ...}}`` (cam.py:176-184); the ``vican`` package need
+  not be installed: its ``SE3`` is mapped onto this package's container while unpickling.
+* ``EdgeAccumulator``: incremental flatten of per-image detection dictionaries as
+  ``estimate_pose_worker`` produces them (cam.py:101-184), so that the solve after the last
+  image starts from arrays (``EdgeTable.from_arrays``) instead of re-walking a dictionary.
+"""
+from __future__ import annotations
+
+import gc
+import pickle
+from typing import Callable, Dict, Iterable, Optional
+
+import numpy as np
+
+from .geometry import SE3
+
+__all__ = ["load_edges", "save_edges", "EdgeAccumulator"]
+
+
+class _RemapUnpickler(pickle.Unpickler):
+    """``vican.geometry.SE3`` -> ``vican_b200.geometry.SE3`` (same attributes: _pose, _R, _t)."""
+
+    def find_class(self, module, name):
+        if module in ("vican.geometry", "geometry") and name == "SE3":
+            return SE3
+        return super().find_class(module, name)
+
+
+class _RemapPickle:
+    """``pickle_module`` for ``torch.load``: the stock module with the remapping unpickler."""
+    __name__ = "vican_b200_remap_pickle"
+    Unpickler = _RemapUnpickler
+    load = staticmethod(lambda f, **kw: _RemapUnpickler(f, **kw).load())
+    loads = staticmethod(pickle.loads)
+    dump = staticmethod(pickle.dump)
+    dumps = staticmethod(pickle.dumps)
+    Pickler = pickle.Pickler
+    PicklingError = pickle.PicklingError
+    UnpicklingError = pickle.UnpicklingError
+    HIGHEST_PROTOCOL = pickle.HIGHEST_PROTOCOL
+    DEFAULT_PROTOCOL = pickle.DEFAULT_PROTOCOL
+
+
+def load_edges(path: str) -> dict:
+    """Edge dictionary from a ``cam_marker_edges.pt`` (reference notebook) or from a file written
+    by ``save_edges``; poses come back as this package's ``SE3``."""
+    import torch
+    gc_was_on = gc.isenabled()
+    gc.disable()            # millions of small objects: keep the cyclic collector out of the load
+    try:
+        return torch.load(path, map_location="cpu", pickle_module=_RemapPickle, weights_only=False)
+    finally:
+        if gc_was_on:
+            gc.enable()
+
+
+def save_edges(edges: dict, path: str) -> None:
+    """Counterpart of the notebook's ``torch.save(edges, path)``."""
+    import torch
+    torch.save(edges, path)
+
+
+class EdgeAccumulator:
+    """Streaming front end of the solver: feed the per-image dictionaries of
+    ``estimate_pose_worker`` (or any ``{(cam, "t_m"): {...}}`` chunk) as they arrive; the
+    callables run once per detection at ``add`` time, and ``table(constraints)`` hands the
+    accumulated arrays to the device ingestion without touching the detections again."""
+
+    def __init__(self, noise_model_r: Callable, noise_model_t: Callable, edge_filter: Callable,
+                 marker_ids: Optional[Iterable[str]] = None):
+        self.noise_model_r, self.noise_model_t, self.edge_filter = noise_model_r, noise_model_t, edge_filter
+        self.marker_ids = None if marker_ids is None else set(marker_ids)     # cam.py:263 id whitelist
+        self._cams, self._tm, self._R, self._t, self._kr, self._kt = [], [], [], [], [], []
+        self._seen: Dict[tuple, int] = {}
+        self.n_dropped = 0
+
+    def __len__(self) -> int:
+        return len(self._cams)
+
+    def add(self, detections: Optional[dict]) -> int:
+        """Returns the number of detections kept from this chunk.  A key seen before replaces the
+        older detection (dictionary-merge semantics of cam.py:263)."""
+        if not detections:
+            return 0
+        kept = 0
+        for key, v in detections.items():
+            if self.marker_ids is not None and key[-1].split("_")[-1] not in self.marker_ids:
+                continue
+            if not self.edge_filter(v):
+                self.n_dropped += 1
+                continue
+            pose = v["pose"]
+            rec = (key[0], key[1], pose.R(), pose.t(), self.noise_model_r(v), self.noise_model_t(v))
+            pos = self._seen.get(key)
+            if pos is None:
+                self._seen[key] = len(self._cams)
+                for lst, x in zip((self._cams, self._tm, self._R, self._t, self._kr, self._kt), rec):
+                    lst.append(x)
+            else:
+                for lst, x in zip((self._cams, self._tm, self._R, self._t, self._kr, self._kt), rec):
+                    lst[pos] = x
+            kept += 1
+        return kept
+
+    def table(self, constraints: dict):
+        from .bipgo import EdgeTable
+        tab = EdgeTable.__new__(EdgeTable)
+        tab._assemble(self._cams, self._tm, list(self._R), list(self._t), self._kr, self._kt, constraints)
+        return tab
