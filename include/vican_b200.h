@@ -104,6 +104,21 @@ int vb_polar_so3_batch(const double* M, double* R, int64_t n, void* stream);
 int vb_svd3_factors_batch(const double* M, double* rot, double* sym_pos, double* sym_inv, int64_t n,
                           void* stream);
 
+/* ---- evaluation helpers (vican/geometry.py:131-172, :264-324; main.ipynb cell 9) ------------ */
+/* optimize_gauge_SE3 (geometry.py:294-324): G = (project_SO3((sum_i Ra_i^T Rb_i)^T),
+ * (1/n) sum_i Rb_i^T (ta_i - tb_i)); with ta == tb == NULL it is optimize_gauge_SO3
+ * (geometry.py:264-291) and gauge_t is not written.  Deterministic two-stage reduction;
+ * gauge_R [9], gauge_t [3] are device pointers. */
+int64_t vb_gauge_workspace_bytes(int64_t n);
+int vb_optimize_gauge(const double* Ra, const double* ta, const double* Rb, const double* tb, int64_t n,
+                      double* gauge_R, double* gauge_t, void* workspace, int64_t workspace_bytes, void* stream);
+/* distance_SO3 (geometry.py:154-172): angle(R1_i^T R2_i) in degrees, arccos of the clipped
+ * trace as the reference; R2 == NULL gives angle(R1_i) (geometry.py:131-151). */
+int vb_distance_so3_batch(const double* R1, const double* R2, double* deg, int64_t n, void* stream);
+/* One transform applied from the left to n poses: (Rg, tg) @ (R_i, t_i)  (cell 9: G.inv() @ pose). */
+int vb_se3_left_compose_batch(const double* Rg, const double* tg, const double* R, const double* t,
+                              double* Rout, double* tout, int64_t n, int round_f32, void* stream);
+
 /* ---- ingestion (bipgo.py:203-276, :420-431) ---------------------------------------------- */
 /* Raw detections are given as flat arrays (already filtered by edge_filter on the host):
  * cam/time/marker indices, detection rotation R[E_raw][9], weights k_r, k_t.  markerC[m] =

@@ -258,3 +258,33 @@ def solve_arrays_oracle(cam, time, marker, R, t, k_r, k_t, marker_R, marker_t_in
     x, _ = solve_translations(J, t_tilde, lsqr_solver)
     x = x.reshape(-1, 3)
     return Rw_c, Rw_t, x[:n_c], x[n_c:]
+
+
+# ------------------------------------------------------- evaluation helpers (geometry.py)
+def angle_deg_oracle(R: np.ndarray) -> np.ndarray:
+    """geometry.py:131-151 ``angle``: degrees(arccos(clip((trace(r) - 1) / 2, -1, 1))), batched."""
+    R = np.asarray(R, dtype=np.float64).reshape(-1, 3, 3)
+    return np.rad2deg(np.arccos(np.clip((np.trace(R, axis1=1, axis2=2) - 1.0) / 2.0, -1.0, 1.0)))
+
+
+def distance_SO3_oracle(R1: np.ndarray, R2: np.ndarray) -> np.ndarray:
+    """geometry.py:154-172 ``distance_SO3``: angle(r1.T @ r2), batched."""
+    R1 = np.asarray(R1, dtype=np.float64).reshape(-1, 3, 3)
+    R2 = np.asarray(R2, dtype=np.float64).reshape(-1, 3, 3)
+    return angle_deg_oracle(np.transpose(R1, (0, 2, 1)) @ R2)
+
+
+def optimize_gauge_SE3_oracle(Ra, ta, Rb, tb):
+    """geometry.py:294-324 ``optimize_gauge_SE3`` on stacked arrays: sum = sum a.R^T b.R
+    (:317), gauge_t = sum b.R^T (a.t - b.t) / n (:318, :322), gauge_r = project_SO3(sum^T)
+    (:320-321).  ``ta = tb = None`` gives ``optimize_gauge_SO3`` (:264-291)."""
+    Ra = np.asarray(Ra, dtype=np.float64).reshape(-1, 3, 3)
+    Rb = np.asarray(Rb, dtype=np.float64).reshape(-1, 3, 3)
+    s = (np.transpose(Ra, (0, 2, 1)) @ Rb).sum(axis=0)
+    u, _, vh = np.linalg.svd(s.T)
+    gr = u @ np.diag([1.0, 1.0, np.linalg.det(u @ vh)]) @ vh
+    if ta is None:
+        return gr, None
+    d = np.asarray(ta, dtype=np.float64).reshape(-1, 3) - np.asarray(tb, dtype=np.float64).reshape(-1, 3)
+    gt = np.einsum("nji,nj->ni", Rb, d).sum(axis=0) / Ra.shape[0]
+    return gr, gt

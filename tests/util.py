@@ -15,7 +15,9 @@ TRANS_REL_TOL = 1e-6
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Solver goldens (network / object cases); ``eval_*.npz`` belong to the evaluation helpers."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if n.startswith(("net_", "obj_"))]
 
 
 def load_golden(name):

@@ -60,6 +60,10 @@ SIGNATURES = {
     "vb_se3_invert_batch": (C.c_int, [VP, VP, VP, VP, I64, C.c_int, VP]),
     "vb_polar_so3_batch": (C.c_int, [VP, VP, I64, VP]),
     "vb_svd3_factors_batch": (C.c_int, [VP, VP, VP, VP, I64, VP]),
+    "vb_gauge_workspace_bytes": (I64, [I64]),
+    "vb_optimize_gauge": (C.c_int, [VP, VP, VP, VP, I64, VP, VP, VP, I64, VP]),
+    "vb_distance_so3_batch": (C.c_int, [VP, VP, VP, I64, VP]),
+    "vb_se3_left_compose_batch": (C.c_int, [VP, VP, VP, VP, VP, VP, I64, C.c_int, VP]),
     "vb_ingest_workspace_bytes": (I64, [I64]),
     "vb_ingest_sort": (C.c_int, [VP, VP, I64, I64, I64, VP, VP, c_i64p, VP, I64, VP]),
     "vb_ingest_max_tiles": (I64, [I64, I64, I64]),

@@ -2,6 +2,7 @@
 #include "../../include/vican_b200.h"
 
 #include "common.cuh"
+#include "evaluate.cuh"
 #include "ingest.cuh"
 #include "lobpcg.cuh"
 #include "lsqr.cuh"
@@ -102,6 +103,37 @@ int vb_polar_so3_batch(const double* M, double* R, int64_t n, void* stream) {
 int vb_svd3_factors_batch(const double* M, double* rot, double* sym_pos, double* sym_inv, int64_t n, void* stream) {
     if (n <= 0) return 0;
     svd_factors_batch_kernel<<<node_grid(n), NODE_THREADS, 0, (cudaStream_t)stream>>>(M, rot, sym_pos, sym_inv, n);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- evaluation
+int64_t vb_gauge_workspace_bytes(int64_t n) { return (int64_t)ev_grid(n) * 12 * (int64_t)sizeof(double); }
+
+int vb_optimize_gauge(const double* Ra, const double* ta, const double* Rb, const double* tb, int64_t n, double* gauge_R,
+                      double* gauge_t, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (n <= 0 || (ta == nullptr) != (tb == nullptr) || (ta != nullptr && gauge_t == nullptr)) return VB_STATUS_BAD_ARGUMENT;
+    if (workspace_bytes < vb_gauge_workspace_bytes(n)) return VB_STATUS_BAD_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = ev_grid(n);
+    gauge_partial_kernel<<<nb, EV_THREADS, 0, st>>>(Ra, ta, Rb, tb, n, (double*)workspace);
+    gauge_finish_kernel<<<1, 32, 0, st>>>((const double*)workspace, nb, n, gauge_R, ta ? gauge_t : nullptr);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int vb_distance_so3_batch(const double* R1, const double* R2, double* deg, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    distance_so3_kernel<<<(int)((n + EV_THREADS - 1) / EV_THREADS), EV_THREADS, 0, (cudaStream_t)stream>>>(R1, R2, deg, n);
+    VB_KERNEL_CHECK();
+    return 0;
+}
+
+int vb_se3_left_compose_batch(const double* Rg, const double* tg, const double* R, const double* t, double* Rout,
+                              double* tout, int64_t n, int round_f32, void* stream) {
+    if (n <= 0) return 0;
+    se3_left_compose_kernel<<<(int)((n + EV_THREADS - 1) / EV_THREADS), EV_THREADS, 0, (cudaStream_t)stream>>>(
+        Rg, tg, R, t, Rout, tout, n, round_f32);
     VB_KERNEL_CHECK();
     return 0;
 }

@@ -18,7 +18,8 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["SE3", "project_SO3", "geodesic_rad", "rel_translation_err"]
+__all__ = ["SE3", "project_SO3", "geodesic_rad", "rel_translation_err", "angle", "distance_SO3", "optimize_gauge_SO3",
+           "optimize_gauge_SE3", "evaluate_against"]
 
 
 class SE3:
@@ -102,3 +103,62 @@ def rel_translation_err(ta: np.ndarray, tb: np.ndarray) -> np.ndarray:
     ta = np.asarray(ta, dtype=np.float64).reshape(-1, 3)
     tb = np.asarray(tb, dtype=np.float64).reshape(-1, 3)
     return np.linalg.norm(ta - tb, axis=-1) / np.maximum(np.linalg.norm(tb, axis=-1), 1e-12)
+
+
+# ---- evaluation helpers with the reference's signatures (geometry.py:131-172, :264-324); the
+# ---- arithmetic runs in the CUDA extension (vican_b200.ops), there is no host fallback
+def angle(r: np.ndarray) -> float:
+    """Rotation angle of a 3x3 rotation in degrees (reference ``angle``, geometry.py:131-151)."""
+    from . import ops
+    return float(ops.distance_so3_batch(np.asarray(r, dtype=np.float64).reshape(1, 3, 3)).cpu()[0])
+
+
+def distance_SO3(r1: np.ndarray, r2: np.ndarray) -> float:
+    """Angle between two rotations in degrees (reference ``distance_SO3``, geometry.py:154-172)."""
+    from . import ops
+    r1, r2 = np.asarray(r1), np.asarray(r2)
+    assert r1.shape == (3, 3) and r2.shape == (3, 3)
+    return float(ops.distance_so3_batch(r1.reshape(1, 3, 3), r2.reshape(1, 3, 3)).cpu()[0])
+
+
+def optimize_gauge_SO3(poses_a, poses_b) -> np.ndarray:
+    """Rotation aligning ``poses_a`` with ``poses_b @ gauge`` (reference geometry.py:264-291)."""
+    from . import ops
+    assert len(poses_a) == len(poses_b)
+    gR, _ = ops.optimize_gauge_batch(np.array([np.asarray(a, np.float64) for a in poses_a]), None,
+                                     np.array([np.asarray(b, np.float64) for b in poses_b]), None)
+    return gR.cpu().numpy()
+
+
+def optimize_gauge_SE3(poses_a, poses_b) -> "SE3":
+    """Transform aligning ``poses_a`` with ``poses_b @ gauge`` (reference geometry.py:294-324)."""
+    from . import ops
+    assert len(poses_a) == len(poses_b)
+    gR, gt = ops.optimize_gauge_batch(np.array([np.asarray(a.R(), np.float64) for a in poses_a]),
+                                      np.array([np.asarray(a.t(), np.float64) for a in poses_a]),
+                                      np.array([np.asarray(b.R(), np.float64) for b in poses_b]),
+                                      np.array([np.asarray(b.t(), np.float64) for b in poses_b]))
+    return SE3(R=gR.cpu().numpy(), t=gt.cpu().numpy().reshape(3, 1))       # gauge_t is 3x1 in the reference (:315)
+
+
+def evaluate_against(gt: dict, est: dict):
+    """main.ipynb cell 9 as one device batch: gauge alignment of the estimates to the ground
+    truth over the common keys, then per-key rotation error (degrees) and translation error
+    (input units).  ``gt`` / ``est`` map ids to SE3-likes (poses wrt the world).  Returns
+    (keys, r_err_deg [n], t_err [n], G) with numpy arrays and G the gauge as ``SE3``."""
+    from . import ops
+    keys = [k for k in gt.keys() if k in est]
+    Rg = np.array([np.asarray(gt[k].R(), np.float64) for k in keys])
+    tg = np.array([np.asarray(gt[k].t(), np.float64).reshape(3) for k in keys])
+    Re = np.array([np.asarray(est[k].R(), np.float64) for k in keys])
+    te = np.array([np.asarray(est[k].t(), np.float64).reshape(3) for k in keys])
+    # cell 9 aligns the INVERSES: G = optimize_gauge_SE3([gt.inv()], [est.inv()]); est' = G.inv() @ est
+    Rgi, tgi = ops.se3_invert_batch(Rg, tg)
+    Rei, tei = ops.se3_invert_batch(Re, te)
+    GR, Gt = ops.optimize_gauge_batch(Rgi, tgi, Rei, tei)
+    GiR, Git = ops.se3_invert_batch(GR.reshape(1, 3, 3), Gt.reshape(1, 3))
+    Ra, ta = ops.se3_left_compose_batch(GiR[0], Git[0], Re, te)
+    r_err = ops.distance_so3_batch(Rg, Ra).cpu().numpy()
+    import torch
+    t_err = torch.linalg.vector_norm(torch.as_tensor(tg, device=ta.device) - ta, dim=1).cpu().numpy()
+    return keys, r_err, t_err, SE3(R=GR.cpu().numpy(), t=Gt.cpu().numpy())
