@@ -26,6 +26,7 @@ extern "C" {
 #define VB_STATUS_NOT_CONVERGED 1   /* CG hit maxiter (reference: assert exit_code == 0, bipgo.py:478) */
 #define VB_STATUS_EIG_STALLED 2     /* LOBPCG hit max_inner before tol (result still returned) */
 #define VB_STATUS_BAD_ARGUMENT 3
+#define VB_STATUS_SINGULAR 4         /* dense direct solve: Schur complement not positive definite (disconnected graph) */
 
 /* Device-resident bipartite graph of aggregated (camera, time) edges, stored twice:
  * sorted by time node (CSR) and sorted by camera (CSC) with camera tiles for the camera
@@ -202,6 +203,16 @@ int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw
                   const int32_t* t_time, const double* k_t, const double* d_sorted, int64_t n_raw, double* x_c, double* x_t,
                   double atol, double btol, double conlim, int64_t iter_lim, int32_t* h_istop,
                   int32_t* h_iters, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Dense direct solve of the same normal equations for small camera sets (n_c <= 8192; the
+ * "direct" option in accurate mode): time nodes are eliminated in closed form, the n_c x n_c camera
+ * Schur complement is factored by a blocked Cholesky written in this library (no cuSOLVER), and
+ * the minimum-norm minimiser is returned -- the limit of the reference's cg / lsqr iterations
+ * (bipgo.py:477-480), which stop ~1e-5 short of it.  Returns VB_STATUS_SINGULAR if the graph is
+ * disconnected.  Synchronises the stream. */
+int64_t vb_trans_schur_workspace_bytes(int64_t n_c, int64_t n_t);
+int vb_trans_schur_direct(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- multi-GPU (edge-sharded by time-node range, one process per GPU) ---------------------- */
 /* NCCL is resolved at run time (dlopen); the reference has no distributed code, these exist so

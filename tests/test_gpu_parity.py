@@ -301,3 +301,58 @@ def test_accurate_mode_is_close_to_exact_minimiser(cuda):
     assert rel_translation_err(t_acc, t_ref).max() < 5e-2
     # and has zero mean (minimum-norm gauge of the singular normal equations)
     assert np.abs(t_acc.mean(axis=0)).max() < 1e-8 * np.abs(t_acc).max()
+
+
+@pytest.mark.parametrize("shape", [(10, 60, 3, 4, 2), (75, 400, 4, 9, 2), (300, 900, 2, 12, 1)])
+def test_dense_direct_path_is_the_exact_minimiser(cuda, shape):
+    """lsqr_solver='direct', mode='accurate': closed-form elimination of the time nodes + blocked
+    Cholesky of the camera Schur complement (csrc/schur.cuh, no cuSOLVER) against a dense
+    minimum-norm least-squares solve of the SAME system (oracle J, t~ built from the device's
+    rotations).  300 cameras = 10 Cholesky tiles with a ragged last one."""
+    from vican_b200 import solver
+    g = syn.make_camera_network(23, *shape)
+    a = _arrays(g)
+    C_m = np.transpose(g.marker_R, (0, 2, 1)) @ g.marker_R[0]
+    con = {str(m): SE3(R=g.marker_R[m], t=g.marker_t[m]) for m in range(g.n_markers)}
+    t_inv0 = np.stack([np.asarray((con[str(m)].inv() @ con["0"]).t(), np.float64) for m in range(g.n_markers)])
+    r_0m = np.transpose(g.marker_R[0])[None] @ g.marker_R
+    marker_q = np.einsum("mij,mj->mi", r_0m, t_inv0)
+    res = {}
+    for solver_name, mode in (("direct", "accurate"), ("conjugate_gradient", "accurate")):
+        r = solver.solve_arrays(a["cam"], a["time"], a["marker"], a["R"], a["t"], a["k_r"], a["k_t"], C_m, marker_q,
+                                a["n_c"], a["n_t"], 3, solver_name, mode=mode)
+        res[solver_name] = r
+    r = res["direct"]
+    n_c, n_t = a["n_c"], a["n_t"]
+    J, tt = orc.translation_system(a["cam"].astype(np.int64), a["time"].astype(np.int64), a["marker"].astype(np.int64),
+                                   a["t"], a["k_t"], g.marker_R, t_inv0, 0, r.Rw_c.cpu().numpy(), r.Rw_t.cpu().numpy(),
+                                   n_c, n_t, np.arange(n_c), n_c + np.arange(n_t))
+    # min-norm minimiser through the scalar Laplacian: J^T J = L (x) I_3
+    A = (J.T @ J).toarray()[::3, ::3]
+    b = (J.T @ tt).reshape(-1, 3)
+    x = np.linalg.pinv(A, rcond=1e-12, hermitian=True) @ b
+    x_dev = np.concatenate([r.x_c.cpu().numpy(), r.x_t.cpu().numpy()])
+    assert rel_translation_err(x_dev, x).max() < 1e-9
+    assert np.abs(x_dev.mean(axis=0)).max() < 1e-10 * np.abs(x_dev).max()
+    # stationarity of the normal equations and agreement with the iterative accurate mode
+    assert np.abs(A @ x_dev - b).max() < 1e-9 * np.abs(b).max()
+    x_pcg = np.concatenate([res["conjugate_gradient"].x_c.cpu().numpy(), res["conjugate_gradient"].x_t.cpu().numpy()])
+    assert rel_translation_err(x_pcg, x_dev).max() < 1e-7
+
+
+def test_dense_direct_path_reports_disconnected_graphs(cuda):
+    from vican_b200 import solver
+    from vican_b200._cabi import VbError
+    g = syn.make_camera_network(3, 8, 40, 2, 3, 2)
+    a = _arrays(g)
+    # two components: cameras 0..3 only see even time nodes, 4..7 odd ones
+    keep = (a["cam"] < 4) == (a["time"] % 2 == 0)
+    for k in ("cam", "time", "marker", "R", "t", "k_r", "k_t"):
+        a[k] = a[k][keep]
+    C_m = np.transpose(g.marker_R, (0, 2, 1)) @ g.marker_R[0]
+    G = solver.DeviceGraph(a["cam"], a["time"], a["marker"], a["R"], a["k_r"], a["k_t"], C_m, a["n_c"], a["n_t"])
+    rot = solver.RotationResult(torch.eye(3, dtype=torch.float64, device="cuda").reshape(1, 9).repeat(a["n_c"], 1),
+                                torch.eye(3, dtype=torch.float64, device="cuda").reshape(1, 9).repeat(a["n_t"], 1), None, 0)
+    with pytest.raises(VbError) as ei:
+        solver.solve_translations(G, rot, a["t"], np.zeros((g.n_markers, 3)), "direct", mode="accurate")
+    assert ei.value.code == 4

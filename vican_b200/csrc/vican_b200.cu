@@ -9,6 +9,7 @@
 #include "nccl_shim.cuh"
 #include "passes.cuh"
 #include "rotation.cuh"
+#include "schur.cuh"
 #include "translation.cuh"
 
 using namespace vb;
@@ -73,6 +74,7 @@ const char* vb_status_string(int code) {
         case VB_STATUS_NOT_CONVERGED: return "conjugate gradient did not converge";
         case VB_STATUS_EIG_STALLED: return "eigen-iteration hit max_inner before reaching tol";
         case VB_STATUS_BAD_ARGUMENT: return "bad argument / workspace too small";
+        case VB_STATUS_SINGULAR: return "camera Schur complement is not positive definite (disconnected graph?)";
         default: return "unknown status";
     }
 }
@@ -331,6 +333,13 @@ int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw
     if (h_istop) *h_istop = (int32_t)hs[LS_ISTOP];
     if (h_iters) *h_iters = (int32_t)hs[LS_ITN];
     return 0;
+}
+
+int64_t vb_trans_schur_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_schur(nullptr, n_c, n_t).bytes; }
+
+int vb_trans_schur_direct(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+    return trans_schur_direct(g, rhs_c, rhs_t, x_c, x_t, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------ multi-GPU

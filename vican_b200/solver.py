@@ -19,6 +19,7 @@ from ._cabi import VbGraph, VbSo3Options, VbSo3Stats, check
 
 F64 = torch.float64
 I32 = torch.int32
+SCHUR_MAX_CAMERAS = 4096      # dense direct translation solve: n_c^2 doubles (128 MB at the cap)
 
 
 class ConvergenceError(AssertionError, RuntimeError):
@@ -224,8 +225,10 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
                        mode: str = "parity", comm: Optional[Comm] = None) -> TranslationResult:
     """``lsqr_solver``: "conjugate_gradient" | "direct" (reference names, bipgo.py:476-480).
     ``mode``: "parity" replays scipy's truncated iterations (what the reference returns);
-    "accurate" runs Jacobi-preconditioned CG to 1e-12 (closer to the true minimiser, and
-    therefore up to ~4e-3 away from the reference's CG answer -- SURVEY.md 7.3-1)."""
+    "accurate" returns the minimum-norm minimiser itself (up to ~4e-3 away from the reference's
+    truncated CG answer -- SURVEY.md 7.3-1): Jacobi-preconditioned CG to 1e-12 for
+    "conjugate_gradient", a dense Cholesky of the camera Schur complement for "direct"
+    (single GPU, n_c <= SCHUR_MAX_CAMERAS; larger or sharded graphs use the PCG)."""
     if lsqr_solver not in ("conjugate_gradient", "direct"):
         raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
     lib = _cabi.lib()
@@ -247,6 +250,14 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
         x_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
         iters = C.c_int32(0)
         istop = C.c_int32(0)
+        if lsqr_solver == "direct" and mode == "accurate" and comm is None and g.n_c <= SCHUR_MAX_CAMERAS:
+            # dense block path (north_star (3)): closed-form elimination of the time nodes + Cholesky of the
+            # n_c x n_c camera Schur complement, written in the extension (no cuSOLVER)
+            wsb = int(lib.vb_trans_schur_workspace_bytes(g.n_c, g.n_t))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            check(lib.vb_trans_schur_direct(C.byref(g.cgraph), _ptr(rhs_c), _ptr(rhs_t), _ptr(x_c), _ptr(x_t), _ptr(ws),
+                                            wsb, _stream()), "vb_trans_schur_direct")
+            return TranslationResult(x_c, x_t, 0, 0)
         if need_rows:
             if comm is not None:
                 raise NotImplementedError("lsqr_solver='direct' is the small-graph path (single GPU)")
