@@ -66,6 +66,9 @@ typedef struct vb_so3_options {
     void*   allreduce_ctx;
     int32_t profile_events; /* != 0: bracket every edge-pass launch with CUDA events (stats->*_pass_ms) */
     int32_t reserved;
+    void*   peer_ctx;       /* vb_peer_create context: the camera pass runs FUSED with its cross-rank sum over
+                             * NVLink peer memory (allreduce / allreduce_ctx are then used for the few other
+                             * reductions only and may point at vb_peer_allreduce); NULL: separate collective */
 } vb_so3_options;
 
 typedef struct vb_so3_stats {
@@ -223,6 +226,19 @@ int vb_nccl_init(const void* h_id128, int64_t bytes, int rank, int nranks, void*
 int vb_nccl_destroy(void* ctx);
 int vb_nccl_allreduce(void* ctx, double* buf, int64_t count, void* stream);   /* a vb_allreduce_fn */
 void* vb_nccl_allreduce_fn(void);
+/* One-shot all-reduce over NVLink peer memory (CUDA IPC windows, all ranks on one box, <= 8):
+ * every rank sums the partials straight out of its peers' windows in rank order, so the result is
+ * bitwise identical everywhere; one kernel, no staging copy.  vb_peer_create allocates this rank's
+ * window (capacity_doubles per buffer; the only device allocation the library ever makes) and
+ * returns its 64-byte IPC handle; after an all-gather of the handles vb_peer_connect maps the
+ * others.  The caller must barrier between connect and first use and before destroy.
+ * vb_peer_allreduce is a vb_allreduce_fn; with vb_so3_options.peer_ctx the exchange is the epilogue
+ * of the camera-pass kernel itself. */
+int vb_peer_create(int rank, int nranks, int64_t capacity_doubles, void** ctx_out, void* h_handle_out64);
+int vb_peer_connect(void* ctx, const void* h_all_handles /* nranks x 64 bytes */);
+int vb_peer_destroy(void* ctx);
+int vb_peer_allreduce(void* ctx, double* buf, int64_t count, void* stream);
+void* vb_peer_allreduce_fn(void);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,26 @@ def main_gpu():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     comm = vdist.create_comm()
+    want_peer = os.environ.get("VICAN_B200_COLLECTIVE", "peer") == "peer"
+    assert (comm.peer is not None) == want_peer, "peer windows expected on a single NVLink box"
+    if comm.peer is not None:
+        # one-shot peer-memory all-reduce (csrc/peer.cuh) against NCCL, 30 back-to-back calls of mixed
+        # sizes (both buffer parities, odd lengths, the full capacity); result bitwise equal on all ranks
+        from vican_b200 import _cabi
+        lib = _cabi.lib()
+        gen = torch.Generator(device=dev).manual_seed(100 + rank)
+        sizes = [1, 7, 1000, 9 * 600, 3 * 600 + 8, 12345, comm.peer_capacity] * 4 + [3, 2]
+        for i, n in enumerate(sizes):
+            x = torch.randn(n, dtype=torch.float64, device=dev, generator=gen)
+            ref = x.clone()
+            dist.all_reduce(ref)
+            comm.allreduce(lib, x)
+            assert (x - ref).abs().max().item() <= 1e-13 * max(1.0, ref.abs().max().item()), (i, n)
+            same = [torch.empty_like(x) for _ in range(world)]
+            dist.all_gather(same, x)
+            assert all(torch.equal(same[0], s) for s in same), "peer all-reduce must be bitwise identical on all ranks"
+        if rank == 0:
+            print("PEER_ALLREDUCE_OK")
     seed, n_c, n_t, d, maxiter = 7, 600, 24_000, 30, 5
     lo, hi = vdist.shard_range(n_t, rank, world)
     det = make_scaled_network(seed, n_c, n_t, d, lo, hi, block=4000, device=dev)
@@ -90,8 +110,8 @@ def main_gpu():
         et = geodesic_rad(torch.cat(parts_R).cpu().numpy(), ref.Rw_t.cpu().numpy()).max()
         xc = rel_translation_err(res.x_c.cpu().numpy(), ref.x_c.cpu().numpy()).max()
         xt = rel_translation_err(torch.cat(parts_x).cpu().numpy(), ref.x_t.cpu().numpy()).max()
-        print("DIST_GPU world=%d rot_c=%.2e rot_t=%.2e x_c=%.2e x_t=%.2e cg_iters=%d/%d" %
-              (world, ec, et, xc, xt, res.trans.iters, ref.trans.iters))
+        print("DIST_GPU world=%d collective=%s rot_c=%.2e rot_t=%.2e x_c=%.2e x_t=%.2e cg_iters=%d/%d" %
+              (world, "peer(fused)" if comm.peer is not None else "nccl", ec, et, xc, xt, res.trans.iters, ref.trans.iters))
         ok = ec < 1e-9 and et < 1e-9 and xc < 1e-8 and xt < 1e-8 and res.trans.iters == ref.trans.iters
         print("DIST_GPU_OK" if ok else "DIST_GPU_FAIL")
     vdist.destroy_comm(comm)

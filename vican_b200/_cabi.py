@@ -40,7 +40,7 @@ class VbGraph(C.Structure):
 
 class VbSo3Options(C.Structure):
     _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP),
-                ("profile_events", I32), ("reserved", I32)]
+                ("profile_events", I32), ("reserved", I32), ("peer_ctx", VP)]
 
 
 class VbSo3Stats(C.Structure):
@@ -95,6 +95,11 @@ SIGNATURES = {
     "vb_nccl_destroy": (C.c_int, [VP]),
     "vb_nccl_allreduce_fn": (VP, []),
     "vb_nccl_allreduce": (C.c_int, [VP, VP, I64, VP]),
+    "vb_peer_create": (C.c_int, [C.c_int, C.c_int, I64, C.POINTER(VP), VP]),
+    "vb_peer_connect": (C.c_int, [VP, VP]),
+    "vb_peer_destroy": (C.c_int, [VP]),
+    "vb_peer_allreduce": (C.c_int, [VP, VP, I64, VP]),
+    "vb_peer_allreduce_fn": (VP, []),
 }
 
 

@@ -34,6 +34,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace vb {
 
@@ -196,14 +197,11 @@ __device__ __forceinline__ void item_fma(const Item& it, const double (&b)[5][3]
 //   FMA(item k)  ->  TMA issue(item k+2)  ->  wait + loads(item k+1)  ->  epilogue(segment of k, if it ends)
 // so the segment reduction / store overlaps the gather round trip of the next item and the TMA copy
 // of an item has one full iteration to land.
-template <int MODE, int CTAS>
-__global__ void __launch_bounds__(PASS_THREADS, CTAS)
-edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ idx,
-                 const double* __restrict__ B, const double* __restrict__ G, const double* __restrict__ lamT,
-                 double* __restrict__ out, int n_seg, const double* __restrict__ skip_flag) {
-    // speculatively enqueued launches (the host polls the eigen-solver's convergence flag one
-    // iteration late) turn into no-ops once the flag is set
-    if (skip_flag != nullptr && *skip_flag != 0.0) return;
+template <int MODE>
+__device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
+                                               const int* __restrict__ idx, const double* __restrict__ B,
+                                               const double* __restrict__ G, const double* __restrict__ lamT,
+                                               double* __restrict__ out, int n_seg) {
     extern __shared__ __align__(128) unsigned char pass_smem[];
     constexpr bool TR = (MODE != 2);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -318,6 +316,35 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
     }
 }
 
+template <int MODE, int CTAS>
+__global__ void __launch_bounds__(PASS_THREADS, CTAS)
+edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ idx,
+                 const double* __restrict__ B, const double* __restrict__ G, const double* __restrict__ lamT,
+                 double* __restrict__ out, int n_seg, const double* __restrict__ skip_flag) {
+    // speculatively enqueued launches (the host polls the eigen-solver's convergence flag one
+    // iteration late) turn into no-ops once the flag is set
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;
+    edge_pass_body<MODE>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg);
+}
+
+// Camera pass FUSED with the cross-rank sum of its result (edge-sharded multi-GPU runs): the
+// per-tile atomics accumulate into this rank's peer window, and the kernel's epilogue is the
+// one-shot all-reduce over NVLink peer memory of peer.cuh -- Y_c = sum over ranks, identical bits
+// on every rank, no separate collective launch, no memset of Y.  Cooperative launch (the epilogue
+// spins on the peers' flags, so all CTAs must be resident).
+template <int CTAS>
+__global__ void __launch_bounds__(PASS_THREADS, CTAS)
+edge_pass_fused_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ idx,
+                       const double* __restrict__ B, const double* __restrict__ G, double* __restrict__ Y, long long n_y,
+                       int n_seg, const double* __restrict__ skip_flag, PeerDev pd) {
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;   // identical on every rank (replicated, bitwise equal state)
+    const unsigned long long epoch = pd.ctrl[pd.rank]->epoch + 1ull;
+    double* mine = pd.buf[pd.rank] + (long long)(epoch & 1ull) * pd.cap;
+    edge_pass_body<2>(seg_ptr, seg_node, idx, B, G, nullptr, mine, n_seg);
+    peer_publish(pd, epoch);
+    peer_reduce(pd, epoch, Y, n_y);
+}
+
 // compact [n][9] -> padded [n][12] node blocks (the gather source layout)
 __global__ void pad_blocks_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n,
                                   const double* __restrict__ skip_flag) {
@@ -353,6 +380,27 @@ inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* 
     }
     edge_pass_kernel<MODE, CTAS><<<pass_grid(n_seg, CTAS), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg, skip_flag);
     VB_KERNEL_CHECK();
+    return 0;
+}
+
+// fused camera pass + cross-rank sum (see edge_pass_fused_kernel); Y needs no zeroing
+inline int launch_pass_cam_fused(const int* tile_cam, const int* tile_start, const int* tidx, const double* B,
+                                 const double* W12, double* Y, int64_t n_c, int64_t n_tiles, PeerCtx* peer, cudaStream_t st,
+                                 const double* skip_flag = nullptr) {
+    if (9 * n_c > peer->dev.cap) return 3;   // VB_STATUS_BAD_ARGUMENT
+    constexpr int CTAS = PASS_CTAS_PER_SM;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VB_CHECK(cudaFuncSetAttribute(edge_pass_fused_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
+        attr_set = true;
+    }
+    // every rank must take part even with no local tiles: at least one CTA
+    const int grid = pass_grid(n_tiles < 1 ? 1 : n_tiles, CTAS);
+    long long n_y = 9 * n_c;
+    int n_seg = (int)n_tiles;
+    void* args[] = {(void*)&tile_start, (void*)&tile_cam, (void*)&tidx, (void*)&B, (void*)&W12, (void*)&Y, (void*)&n_y,
+                    (void*)&n_seg, (void*)&skip_flag, (void*)&peer->dev};
+    VB_CHECK(cudaLaunchCooperativeKernel((void*)edge_pass_fused_kernel<CTAS>, dim3(grid), dim3(PASS_THREADS), args, PASS_SMEM, st));
     return 0;
 }
 

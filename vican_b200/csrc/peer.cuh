@@ -1,0 +1,139 @@
+// One-shot all-reduce over NVLink peer memory (edge-sharded multi-GPU runs).
+//
+// Every rank owns one cudaMalloc'ed "window" that all other ranks of the box map through CUDA
+// IPC:  two exchange buffers (parity of the call number) + one flag per peer + counters.
+// An all-reduce of the camera-side accumulator (n_c x 9 doubles = 720 KB at cfg4) is then
+//   1. my partial sums land in MY buffer[parity]           (written by my own kernel)
+//   2. the last CTA to finish publishes  flag[me] = epoch  into every peer's window
+//      (fence.sys + st.release.sys over NVLink)
+//   3. every CTA waits until all flags in its OWN window reached the epoch (ld.acquire.sys),
+//      then sums its slice of the 8 partials straight out of the peers' windows in rank order
+//      -> the result is bitwise identical on all ranks (the replicated LOBPCG / SVD steps
+//      depend on that) and no data is ever staged or copied twice.
+// The other-parity buffer of my window is cleared in step 3 for the next call, which is safe
+// because every peer finished reading it before it published the flag I just waited for.
+//
+// Two users: peer_allreduce_kernel (generic vb_allreduce_fn for small vectors: CG, degrees) and
+// edge_pass_fused_kernel in passes.cuh, where steps 2-3 are the EPILOGUE of the camera pass itself
+// (the per-tile atomics accumulate directly into the window).  Both are launched cooperatively:
+// the spin in step 3 requires all CTAs of the grid to be resident.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int PEER_MAX = 8;
+constexpr int PEER_AR_THREADS = 256;
+constexpr int PEER_AR_CTAS = 64;
+
+struct PeerCtrl {            // lives at the start of every window
+    unsigned long long flags[PEER_MAX];   // flags[r]: latest epoch rank r published (written by rank r)
+    unsigned long long epoch;             // calls completed by this rank
+    unsigned int done;                    // CTAs that finished step 1
+    unsigned int done2;                   // CTAs that finished step 3
+    unsigned int pad[2];
+};
+constexpr size_t PEER_CTRL_BYTES = 256;   // >= sizeof(PeerCtrl), keeps the buffers 256-byte aligned
+
+struct PeerDev {             // kernel argument
+    int rank, world;
+    long long cap;                        // doubles per buffer
+    PeerCtrl* ctrl[PEER_MAX];             // every rank's window (ctrl[rank] = mine)
+    double* buf[PEER_MAX];                // buffer 0 of every window; buffer 1 = buf + cap
+};
+
+struct PeerCtx {
+    PeerDev dev;
+    void* base = nullptr;
+    void* opened[PEER_MAX] = {nullptr};
+    size_t bytes = 0;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 ld_peer2(const double* p) {
+    double2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+// Step 2 (called by ALL threads of a CTA after its last write to the window): returns when this
+// CTA may proceed to the wait.  The last CTA of the grid publishes the epoch to every peer.
+__device__ __forceinline__ void peer_publish(const PeerDev& pd, unsigned long long epoch) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PeerCtrl* me = pd.ctrl[pd.rank];
+        const unsigned int old = atomicAdd(&me->done, 1u);
+        if (old == gridDim.x - 1) {
+            __threadfence_system();
+            for (int r = 0; r < pd.world; ++r) st_release_sys(&pd.ctrl[r]->flags[pd.rank], epoch);
+        }
+    }
+}
+
+// Step 3: wait for all ranks, then out[i] = sum_r window_r[parity][i] for this CTA's share of
+// [0, count), clear my other-parity buffer, and let the last CTA advance the epoch.
+__device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long long epoch, double* __restrict__ out, long long count) {
+    PeerCtrl* me = pd.ctrl[pd.rank];
+    if (threadIdx.x < pd.world) {
+        const unsigned long long* f = &me->flags[threadIdx.x];
+        while (ld_acquire_sys(f) < epoch) { }
+    }
+    __syncthreads();
+    const long long par = (long long)(epoch & 1ull) * pd.cap;
+    const long long npair = (count + 1) >> 1;                 // buffers are padded to an even length
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int r = 0; r < pd.world; ++r) {
+            const double2 v = ld_peer2(pd.buf[r] + par + 2 * i);
+            s.x += v.x; s.y += v.y;
+        }
+        out[2 * i] = s.x;
+        if (2 * i + 1 < count) out[2 * i + 1] = s.y;
+    }
+    double* other = pd.buf[pd.rank] + ((long long)((epoch + 1ull) & 1ull)) * pd.cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pd.cap; i += stride) other[i] = 0.0;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(&me->done2, 1u);
+        if (old == gridDim.x - 1) {
+            me->done = 0u; me->done2 = 0u;
+            __threadfence();
+            me->epoch = epoch;
+        }
+    }
+}
+
+// generic in-place all-reduce of a small vector (count <= cap)
+__global__ void __launch_bounds__(PEER_AR_THREADS) peer_allreduce_kernel(PeerDev pd, double* __restrict__ data, long long count) {
+    const unsigned long long epoch = pd.ctrl[pd.rank]->epoch + 1ull;   // advanced by the previous call's last CTA
+    double* mine = pd.buf[pd.rank] + (long long)(epoch & 1ull) * pd.cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) mine[i] = data[i];
+    peer_publish(pd, epoch);
+    peer_reduce(pd, epoch, data, count);
+}
+
+inline int launch_peer_allreduce(PeerCtx* ctx, double* data, int64_t count, cudaStream_t st) {
+    if (count <= 0) return 0;
+    if (count > ctx->dev.cap) return 3;   // VB_STATUS_BAD_ARGUMENT
+    int grid = (int)((count + PEER_AR_THREADS - 1) / PEER_AR_THREADS);
+    if (grid > PEER_AR_CTAS) grid = PEER_AR_CTAS;
+    long long cnt = count;
+    void* args[] = {(void*)&ctx->dev, (void*)&data, (void*)&cnt};
+    VB_CHECK(cudaLaunchCooperativeKernel((void*)peer_allreduce_kernel, dim3(grid), dim3(PEER_AR_THREADS), args, 0, st));
+    return 0;
+}
+
+}  // namespace vb

@@ -213,6 +213,15 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         return rc;
     };
     auto cam_pass = [&](const double* Wt, double* Y, const double* skip = nullptr) -> int {
+        if (opt->peer_ctx != nullptr) {   // camera pass fused with its cross-rank sum (peer windows over NVLink)
+            S->cam_passes++; S->kernel_launches++;
+            const int slot = prof_begin(1);
+            int rc = launch_pass_cam_fused(g->tile_cam, g->tile_start, g->c_time, g->c_B, Wt, Y, n_c, g->n_tiles,
+                                           (PeerCtx*)opt->peer_ctx, st, skip);
+            prof_end(slot);
+            last_cam_slot = slot;
+            return rc;
+        }
         VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
         S->cam_passes++; S->kernel_launches++;
         const int slot = prof_begin(1);

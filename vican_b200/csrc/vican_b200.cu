@@ -8,6 +8,7 @@
 #include "lsqr.cuh"
 #include "nccl_shim.cuh"
 #include "passes.cuh"
+#include "peer.cuh"
 #include "rotation.cuh"
 #include "schur.cuh"
 #include "translation.cuh"
@@ -378,5 +379,61 @@ int vb_nccl_allreduce(void* ctx, double* buf, int64_t count, void* stream) {
 }
 
 void* vb_nccl_allreduce_fn(void) { return (void*)&vb_nccl_allreduce; }
+
+// ---- peer-memory windows (CUDA IPC over NVLink) ----
+int vb_peer_create(int rank, int nranks, int64_t capacity_doubles, void** ctx_out, void* h_handle_out64) {
+    if (nranks < 1 || nranks > PEER_MAX || rank < 0 || rank >= nranks || capacity_doubles < 2) return VB_STATUS_BAD_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    static_assert(sizeof(PeerCtrl) <= PEER_CTRL_BYTES, "control block");
+    PeerCtx* ctx = new PeerCtx();
+    const int64_t cap = (capacity_doubles + 31) & ~(int64_t)31;   // even (16-byte loads) and 256-byte aligned buffers
+    ctx->bytes = PEER_CTRL_BYTES + 2 * (size_t)cap * sizeof(double);
+    cudaError_t e = cudaMalloc(&ctx->base, ctx->bytes);
+    if (e == cudaSuccess) e = cudaMemset(ctx->base, 0, ctx->bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ctx->base);
+    if (e != cudaSuccess) { if (ctx->base) cudaFree(ctx->base); delete ctx; return -(int)e; }
+    memcpy(h_handle_out64, &h, sizeof(h));
+    ctx->dev.rank = rank; ctx->dev.world = nranks; ctx->dev.cap = cap;
+    for (int r = 0; r < PEER_MAX; ++r) { ctx->dev.ctrl[r] = nullptr; ctx->dev.buf[r] = nullptr; }
+    ctx->dev.ctrl[rank] = (PeerCtrl*)ctx->base;
+    ctx->dev.buf[rank] = (double*)((char*)ctx->base + PEER_CTRL_BYTES);
+    *ctx_out = ctx;
+    return 0;
+}
+
+int vb_peer_connect(void* vctx, const void* h_all_handles) {
+    PeerCtx* ctx = (PeerCtx*)vctx;
+    if (!ctx) return VB_STATUS_BAD_ARGUMENT;
+    for (int r = 0; r < ctx->dev.world; ++r) {
+        if (r == ctx->dev.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)h_all_handles + 64 * (size_t)r, sizeof(h));
+        void* p = nullptr;
+        VB_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->opened[r] = p;
+        ctx->dev.ctrl[r] = (PeerCtrl*)p;
+        ctx->dev.buf[r] = (double*)((char*)p + PEER_CTRL_BYTES);
+    }
+    return 0;
+}
+
+int vb_peer_destroy(void* vctx) {
+    PeerCtx* ctx = (PeerCtx*)vctx;
+    if (!ctx) return 0;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < PEER_MAX; ++r)
+        if (ctx->opened[r]) cudaIpcCloseMemHandle(ctx->opened[r]);
+    if (ctx->base) cudaFree(ctx->base);
+    delete ctx;
+    return 0;
+}
+
+int vb_peer_allreduce(void* ctx, double* buf, int64_t count, void* stream) {
+    return launch_peer_allreduce((PeerCtx*)ctx, buf, count, (cudaStream_t)stream);
+}
+
+void* vb_peer_allreduce_fn(void) { return (void*)&vb_peer_allreduce; }
 
 }  // extern "C"

@@ -38,8 +38,12 @@ def init_process_group_from_env(backend: Optional[str] = None):
     return rank, world
 
 
-def create_comm() -> Optional[Comm]:
-    """NCCL communicator of the extension for the current process group (None on 1 rank)."""
+def create_comm(peer_capacity_doubles: int = 9 * 16384 + 64) -> Optional[Comm]:
+    """Communicator of the extension for the current process group (None on 1 rank): an NCCL
+    communicator plus, when every rank can map its peers (one box, <= 8 GPUs, CUDA IPC), the
+    NVLink peer-memory windows of csrc/peer.cuh sized for ``peer_capacity_doubles`` per exchange
+    (default: the camera accumulator of 16 k cameras).  ``VICAN_B200_COLLECTIVE=nccl`` disables
+    the windows."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return None
@@ -55,12 +59,42 @@ def create_comm() -> Optional[Comm]:
     idbuf = C.create_string_buffer(obj[0], 128)
     ctx = C.c_void_p()
     _cabi.check(lib.vb_nccl_init(idbuf, 128, rank, world, C.byref(ctx)), "vb_nccl_init")
-    return Comm(ctx.value, rank, world)
+    comm = Comm(ctx.value, rank, world)
+    # NVLink peer-memory windows for the one-shot / fused all-reduce (csrc/peer.cuh).  All ranks must
+    # agree: the windows are used only if EVERY rank could map every other rank's window.
+    mode = os.environ.get("VICAN_B200_COLLECTIVE", "peer").lower()
+    if mode not in ("peer", "nccl"):
+        raise ValueError("VICAN_B200_COLLECTIVE must be 'peer' or 'nccl'")
+    if mode == "peer" and world <= 8:
+        cap = int(peer_capacity_doubles)
+        pctx, handle = C.c_void_p(), C.create_string_buffer(64)
+        ok = lib.vb_peer_create(rank, world, cap, C.byref(pctx), handle) == 0
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw) if ok else None)
+        if ok and all(h is not None for h in handles):
+            ok = lib.vb_peer_connect(pctx, C.create_string_buffer(b"".join(handles), 64 * world)) == 0
+        else:
+            ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))          # also the barrier between connect and first use
+        if all(flags):
+            comm.peer, comm.peer_capacity = pctx.value, cap
+        elif pctx.value:
+            lib.vb_peer_destroy(pctx)
+    return comm
 
 
 def destroy_comm(comm: Optional[Comm]):
     if comm is not None:
-        _cabi.load_library().vb_nccl_destroy(comm.ctx)
+        import torch.distributed as dist
+        lib = _cabi.load_library()
+        if comm.peer is not None:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier()                            # nobody may still read a window that is about to be freed
+            lib.vb_peer_destroy(comm.peer)
+            comm.peer = None
+        lib.vb_nccl_destroy(comm.ctx)
 
 
 def shard_range(n_items: int, rank: int, world: int):

@@ -80,10 +80,28 @@ class HostUpload:
 
 @dataclasses.dataclass
 class Comm:
-    """NCCL communicator handle of the extension (edge-sharded multi-GPU runs)."""
+    """Communicator handles of the extension (edge-sharded multi-GPU runs): ``ctx`` = NCCL
+    communicator, ``peer`` = NVLink peer-memory windows (``vb_peer_create``) or None.  With
+    ``peer`` every cross-rank sum is the one-shot kernel of csrc/peer.cuh and the camera pass runs
+    fused with its sum; without it NCCL all-reduces are issued on the solver's stream."""
     ctx: int
     rank: int
     world: int
+    peer: Optional[int] = None
+    peer_capacity: int = 0
+
+    def reducer(self, lib, count: int):
+        """(vb_allreduce_fn, ctx) able to sum ``count`` doubles."""
+        if self.peer is not None and count <= self.peer_capacity:
+            return lib.vb_peer_allreduce_fn(), self.peer
+        return lib.vb_nccl_allreduce_fn(), self.ctx
+
+    def allreduce(self, lib, t: torch.Tensor):
+        n = t.numel()
+        if self.peer is not None and n <= self.peer_capacity:
+            check(lib.vb_peer_allreduce(self.peer, _ptr(t), n, _stream()), "vb_peer_allreduce")
+        else:
+            check(lib.vb_nccl_allreduce(self.ctx, _ptr(t), n, _stream()), "vb_nccl_allreduce")
 
 
 def default_tile_len(n_edges: int, n_sms: int = 148) -> int:
@@ -203,9 +221,9 @@ def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner:
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         r_c = torch.empty((g.n_c, 9), dtype=F64, device=dev)
         r_t = torch.empty((g.n_t, 9), dtype=F64, device=dev)
-        opt = VbSo3Options(int(maxiter), int(max_inner), float(tol),
-                           lib.vb_nccl_allreduce_fn() if comm is not None else None,
-                           comm.ctx if comm is not None else None, 1 if profile_events else 0, 0)
+        fn, fctx = comm.reducer(lib, 9 * g.n_c) if comm is not None else (None, None)
+        fused = comm.peer if (comm is not None and comm.peer is not None and 9 * g.n_c <= comm.peer_capacity) else None
+        opt = VbSo3Options(int(maxiter), int(max_inner), float(tol), fn, fctx, 1 if profile_events else 0, 0, fused)
         stats = VbSo3Stats()
         rc = lib.vb_so3sync_run(C.byref(g.cgraph), C.byref(opt), _ptr(r_c), _ptr(r_t), _ptr(ws), wsb,
                                 C.byref(stats), _stream())
@@ -271,16 +289,15 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
         else:
             if comm is not None and rhs_c is not None:
                 # camera rows of J^T t~ are partial sums over the local edge shard
-                check(lib.vb_nccl_allreduce(comm.ctx, _ptr(rhs_c), 3 * g.n_c, _stream()), "vb_nccl_allreduce")
+                comm.allreduce(lib, rhs_c)
             wsb = int(lib.vb_trans_cg_workspace_bytes(g.n_c, g.n_t))
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             n_unknowns = 3 * (g.n_c + g.n_t)   # global count differs on shards; only the cap depends on it
             jacobi = 1 if mode == "accurate" else 0
             rtol = 1e-12 if mode == "accurate" else 1e-5
+            fn, fctx = comm.reducer(lib, 3 * g.n_c + 8) if comm is not None else (None, None)
             rc = lib.vb_trans_cg(C.byref(g.cgraph), _ptr(rhs_c), _ptr(rhs_t), _ptr(x_c), _ptr(x_t), rtol,
-                                 10 * n_unknowns, jacobi, C.byref(iters), _ptr(ws), wsb,
-                                 lib.vb_nccl_allreduce_fn() if comm is not None else None,
-                                 comm.ctx if comm is not None else None,
+                                 10 * n_unknowns, jacobi, C.byref(iters), _ptr(ws), wsb, fn, fctx,
                                  1 if (comm is None or comm.rank == 0) else 0, _stream())
             if rc == 1:
                 raise ConvergenceError("conjugate gradient did not converge (reference: assert exit_code == 0)")
@@ -292,7 +309,7 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
                 tot = torch.cat([x_c.sum(0) , x_t.sum(0), torch.tensor([float(g.n_t)], dtype=F64, device=dev)])
                 if comm is not None:
                     tot[:3] = 0.0  # camera block is replicated: count it once, below
-                    check(lib.vb_nccl_allreduce(comm.ctx, _ptr(tot), 7, _stream()), "vb_nccl_allreduce")
+                    comm.allreduce(lib, tot)
                     tot[:3] = x_c.sum(0)
                 mean = (tot[:3] + tot[3:6]) / (g.n_c + tot[6])
                 x_c -= mean
