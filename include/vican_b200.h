@@ -26,6 +26,7 @@ extern "C" {
 #define VB_STATUS_NOT_CONVERGED 1   /* CG hit maxiter (reference: assert exit_code == 0, bipgo.py:478) */
 #define VB_STATUS_EIG_STALLED 2     /* LOBPCG hit max_inner before tol (result still returned) */
 #define VB_STATUS_BAD_ARGUMENT 3
+#define VB_STATUS_PEER_TIMEOUT 5     /* peer-memory all-reduce: a rank never arrived (results invalid) */
 #define VB_STATUS_SINGULAR 4         /* dense direct solve: Schur complement not positive definite (disconnected graph) */
 
 /* Device-resident bipartite graph of aggregated (camera, time) edges, stored twice:
@@ -239,6 +240,8 @@ int vb_peer_connect(void* ctx, const void* h_all_handles /* nranks x 64 bytes */
 int vb_peer_destroy(void* ctx);
 int vb_peer_allreduce(void* ctx, double* buf, int64_t count, void* stream);
 void* vb_peer_allreduce_fn(void);
+/* Synchronises the stream; VB_STATUS_PEER_TIMEOUT if any wait on a peer gave up (~10 s) since creation. */
+int vb_peer_status(void* ctx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,8 +33,11 @@ struct PeerCtrl {            // lives at the start of every window
     unsigned long long epoch;             // calls completed by this rank
     unsigned int done;                    // CTAs that finished step 1
     unsigned int done2;                   // CTAs that finished step 3
-    unsigned int pad[2];
+    unsigned int timeouts;                // waits that gave up (a peer never arrived): results are invalid
+    unsigned int pad;
+    unsigned long long dirty[2];          // doubles of buffer 0 / 1 that are not zero (set by the call that used it)
 };
+constexpr long long PEER_SPIN_LIMIT = 20000000000ll;   // clock64 ticks (~10 s): a lost peer becomes an error, not a hung GPU
 constexpr size_t PEER_CTRL_BYTES = 256;   // >= sizeof(PeerCtrl), keeps the buffers 256-byte aligned
 
 struct PeerDev {             // kernel argument
@@ -84,9 +87,14 @@ __device__ __forceinline__ void peer_publish(const PeerDev& pd, unsigned long lo
 // [0, count), clear my other-parity buffer, and let the last CTA advance the epoch.
 __device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long long epoch, double* __restrict__ out, long long count) {
     PeerCtrl* me = pd.ctrl[pd.rank];
+    const int opar = (int)((epoch + 1ull) & 1ull);
+    const long long dirty_other = (long long)me->dirty[opar];   // written by the previous call's last CTA
     if (threadIdx.x < pd.world) {
         const unsigned long long* f = &me->flags[threadIdx.x];
-        while (ld_acquire_sys(f) < epoch) { }
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < epoch) {
+            if (clock64() - t0 > PEER_SPIN_LIMIT) { atomicAdd(&me->timeouts, 1u); break; }
+        }
     }
     __syncthreads();
     const long long par = (long long)(epoch & 1ull) * pd.cap;
@@ -101,14 +109,18 @@ __device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long lon
         out[2 * i] = s.x;
         if (2 * i + 1 < count) out[2 * i + 1] = s.y;
     }
-    double* other = pd.buf[pd.rank] + ((long long)((epoch + 1ull) & 1ull)) * pd.cap;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pd.cap; i += stride) other[i] = 0.0;
+    // the next call may be a fused camera pass that ACCUMULATES into the other buffer: clear what the
+    // call before this one left there (nobody reads it any more, see the header)
+    double* other = pd.buf[pd.rank] + (long long)opar * pd.cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dirty_other; i += stride) other[i] = 0.0;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int old = atomicAdd(&me->done2, 1u);
         if (old == gridDim.x - 1) {
             me->done = 0u; me->done2 = 0u;
+            me->dirty[opar] = 0ull;
+            me->dirty[opar ^ 1] = (unsigned long long)count;
             __threadfence();
             me->epoch = epoch;
         }
@@ -129,6 +141,7 @@ inline int launch_peer_allreduce(PeerCtx* ctx, double* data, int64_t count, cuda
     if (count <= 0) return 0;
     if (count > ctx->dev.cap) return 3;   // VB_STATUS_BAD_ARGUMENT
     int grid = (int)((count + PEER_AR_THREADS - 1) / PEER_AR_THREADS);
+    if (grid < 16) grid = 16;             // even a 3-scalar call may have to clear a camera accumulator (see peer_reduce)
     if (grid > PEER_AR_CTAS) grid = PEER_AR_CTAS;
     long long cnt = count;
     void* args[] = {(void*)&ctx->dev, (void*)&data, (void*)&cnt};

@@ -75,6 +75,7 @@ const char* vb_status_string(int code) {
         case VB_STATUS_NOT_CONVERGED: return "conjugate gradient did not converge";
         case VB_STATUS_EIG_STALLED: return "eigen-iteration hit max_inner before reaching tol";
         case VB_STATUS_BAD_ARGUMENT: return "bad argument / workspace too small";
+        case VB_STATUS_PEER_TIMEOUT: return "a peer rank never arrived at a peer-memory all-reduce (results invalid)";
         case VB_STATUS_SINGULAR: return "camera Schur complement is not positive definite (disconnected graph?)";
         default: return "unknown status";
     }
@@ -435,5 +436,14 @@ int vb_peer_allreduce(void* ctx, double* buf, int64_t count, void* stream) {
 }
 
 void* vb_peer_allreduce_fn(void) { return (void*)&vb_peer_allreduce; }
+
+int vb_peer_status(void* vctx, void* stream) {
+    PeerCtx* ctx = (PeerCtx*)vctx;
+    if (!ctx) return VB_STATUS_BAD_ARGUMENT;
+    unsigned int t = 0;
+    VB_CHECK(cudaMemcpyAsync(&t, &((PeerCtrl*)ctx->base)->timeouts, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VB_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return t == 0 ? VB_STATUS_OK : VB_STATUS_PEER_TIMEOUT;
+}
 
 }  // extern "C"

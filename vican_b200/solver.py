@@ -374,6 +374,8 @@ def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int,
                                 (("Rw_c", Rw_c), ("Rw_t", Rw_t), ("x_c", x_c), ("x_t", x_t)))
     ev[3].record()
     torch.cuda.synchronize()
+    if comm is not None and comm.peer is not None:
+        check(_cabi.lib().vb_peer_status(comm.peer, _stream()), "vb_peer_status")
     phase = dict(ingest=ev[0].elapsed_time(ev[1]), rotation=ev[1].elapsed_time(ev[2]),
                  translation=ev[2].elapsed_time(ev[3]))
     return SolveResult(Rw_c, Rw_t, x_c, x_t, g, rot, tr, phase)
