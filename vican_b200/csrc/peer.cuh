@@ -6,7 +6,7 @@
 //   1. my partial sums land in MY buffer[parity]           (written by my own kernel)
 //   2. the last CTA to finish publishes  flag[me] = epoch  into every peer's window
 //      (fence.sys + st.release.sys over NVLink)
-//   3. every CTA waits until all flags in its OWN window reached the epoch (ld.acquire.sys),
+//   3. every CTA waits until all flags in its OWN window reached the epoch (relaxed polls, one fence),
 //      then sums its slice of the 8 partials straight out of the peers' windows in rank order
 //      -> the result is bitwise identical on all ranks (the replicated LOBPCG / SVD steps
 //      depend on that) and no data is ever staged or copied twice.
@@ -54,12 +54,14 @@ struct PeerCtx {
     size_t bytes = 0;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+// polling load: RELAXED (an ld.acquire.sys compiles to LDG + CCTL.IVALL, i.e. every poll iteration
+// would flush the SM's L1 under the CTAs that are still gathering); the acquire is one fence afterwards
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ double2 ld_peer2(const double* p) {
@@ -71,14 +73,19 @@ __device__ __forceinline__ double2 ld_peer2(const double* p) {
 // Step 2 (called by ALL threads of a CTA after its last write to the window): returns when this
 // CTA may proceed to the wait.  The last CTA of the grid publishes the epoch to every peer.
 __device__ __forceinline__ void peer_publish(const PeerDev& pd, unsigned long long epoch) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();   // cumulative: covers the whole CTA's writes (ordered before this thread by the barrier)
         PeerCtrl* me = pd.ctrl[pd.rank];
         const unsigned int old = atomicAdd(&me->done, 1u);
         if (old == gridDim.x - 1) {
+            // ONE system-scope fence orders every CTA's window writes (made visible to this thread through
+            // the counter) before the flag stores; the stores themselves are relaxed and pipeline over NVLink
+            // (a st.release per peer would serialise 8 fence + round-trip pairs)
             __threadfence_system();
-            for (int r = 0; r < pd.world; ++r) st_release_sys(&pd.ctrl[r]->flags[pd.rank], epoch);
+#pragma unroll
+            for (int r = 0; r < PEER_MAX; ++r)
+                if (r < pd.world) st_relaxed_sys(&pd.ctrl[r]->flags[pd.rank], epoch);
         }
     }
 }
@@ -92,20 +99,26 @@ __device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long lon
     if (threadIdx.x < pd.world) {
         const unsigned long long* f = &me->flags[threadIdx.x];
         const long long t0 = clock64();
-        while (ld_acquire_sys(f) < epoch) {
+        while (ld_relaxed_sys(f) < epoch) {
+            __nanosleep(64);
             if (clock64() - t0 > PEER_SPIN_LIMIT) { atomicAdd(&me->timeouts, 1u); break; }
         }
+        __threadfence_system();   // acquire: the peers' window writes are ordered before their flags
     }
     __syncthreads();
     const long long par = (long long)(epoch & 1ull) * pd.cap;
     const long long npair = (count + 1) >> 1;                 // buffers are padded to an even length
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
+        // all peer loads in flight together (one NVLink round trip, not `world` of them); summed in rank order
+        double2 v[PEER_MAX];
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            if (r < pd.world) v[r] = ld_peer2(pd.buf[r] + par + 2 * i);
         double2 s = make_double2(0.0, 0.0);
-        for (int r = 0; r < pd.world; ++r) {
-            const double2 v = ld_peer2(pd.buf[r] + par + 2 * i);
-            s.x += v.x; s.y += v.y;
-        }
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            if (r < pd.world) { s.x += v[r].x; s.y += v[r].y; }
         out[2 * i] = s.x;
         if (2 * i + 1 < count) out[2 * i + 1] = s.y;
     }
@@ -113,9 +126,9 @@ __device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long lon
     // call before this one left there (nobody reads it any more, see the header)
     double* other = pd.buf[pd.rank] + (long long)opar * pd.cap;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dirty_other; i += stride) other[i] = 0.0;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned int old = atomicAdd(&me->done2, 1u);
         if (old == gridDim.x - 1) {
             me->done = 0u; me->done2 = 0u;
