@@ -242,6 +242,9 @@ int vb_peer_allreduce(void* ctx, double* buf, int64_t count, void* stream);
 void* vb_peer_allreduce_fn(void);
 /* Synchronises the stream; VB_STATUS_PEER_TIMEOUT if any wait on a peer gave up (~10 s) since creation. */
 int vb_peer_status(void* ctx, void* stream);
+/* Diagnostics: globaltimer stamps (ns) of the last exchange on this rank -- [0] publish (last CTA finished
+ * its partial sums), [1] all flags seen by CTA 0, [2] CTA 0 finished its sums, [3] last CTA done.  Synchronises. */
+int vb_peer_stamps(void* ctx, uint64_t* h_out4, void* stream);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ SIGNATURES = {
     "vb_peer_allreduce": (C.c_int, [VP, VP, I64, VP]),
     "vb_peer_allreduce_fn": (VP, []),
     "vb_peer_status": (C.c_int, [VP, VP]),
+    "vb_peer_stamps": (C.c_int, [VP, VP, VP]),
 }
 
 

@@ -28,7 +28,8 @@ namespace cg = cooperative_groups;
 constexpr int LOB_THREADS = 256;
 constexpr int LOB_NRED = 112;      // >= 12*9 + 1
 // persistent small state (doubles)
-constexpr int SM_THETA = 0, SM_RESN = 3, SM_CONV = 6, SM_ANORM = 7, SM_ITERS = 8, SM_ACT = 9, SM_SIZE = 32;
+constexpr int SM_THETA = 0, SM_RESN = 3, SM_CONV = 6, SM_ANORM = 7, SM_ITERS = 8, SM_ACT = 9, SM_TIME = 18, SM_SIZE = 32;
+// SM_TIME..+9: globaltimer stamps (ns) of block 0 at the stage boundaries of the last step (diagnostics)
 
 struct LobpcgParams {
     int n_c;
@@ -95,6 +96,14 @@ __device__ __forceinline__ void blk_times(const double* v, const double* Cm, int
             out[3 * i + j] += v[3 * i] * Cm[j] + v[3 * i + 1] * Cm[ldc + j] + v[3 * i + 2] * Cm[2 * ldc + j];
 }
 
+__device__ __forceinline__ void lob_stamp(const LobpcgParams& p, int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.small[SM_TIME + k] = (double)t;
+    }
+}
+
 __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParams p) {
     // a speculatively enqueued step after convergence is a no-op (uniform across the grid: the flag
     // was written by the previous launch)
@@ -117,6 +126,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     double* part2 = p.partial + ((size_t)gridDim.x + blockIdx.x) * LOB_NRED;
     double* part3 = p.partial + ((size_t)2 * gridDim.x + blockIdx.x) * LOB_NRED;
 
+    lob_stamp(p, 0);
     // ---------------- stage 1: A-image of the applied block, Gram matrices -----------------
     {
         double* V = p.first ? p.X : p.W;
@@ -154,8 +164,11 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
                 block_reduce_store<9>(m, red_sm, part1 + 54 + 9 * blk);
             }
     }
+    lob_stamp(p, 1);
     grid.sync();
+    lob_stamp(p, 2);
     grid_combine(base1, 109, tot);
+    lob_stamp(p, 3);
 
     // ---------------- stage 2: Rayleigh-Ritz (redundant per CTA, deterministic) ------------
     // one warp per CTA: warp-cooperative 9x9 solve (parallel-ordered Jacobi), dense_small.cuh
@@ -179,6 +192,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
         ritz9_coop(Gm, Mm, act_s, Cx, Cp, theta_s, actP_s, work, iwork, lane, 32);
     }
     __syncthreads();
+    lob_stamp(p, 4);
 
     // ---------------- stage 3: basis update, residual, preconditioned direction ------------
     const double anorm = sqrt(tot[108] / (3.0 * n_c));
@@ -218,8 +232,10 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
         }
         block_reduce_store<21>(acc, red_sm, part2);
     }
+    lob_stamp(p, 5);
     grid.sync();
     grid_combine(base2, 21, tot);
+    lob_stamp(p, 6);
     if (threadIdx.x == 0) {
         const double r0 = sqrt(tot[18]), r1 = sqrt(tot[19]), r2 = sqrt(tot[20]);
         const double rmax = fmax(r0, fmax(r1, r2));
@@ -262,8 +278,10 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
         }
         block_reduce_store<27>(acc, red_sm, part3);
     }
+    lob_stamp(p, 7);
     grid.sync();
     grid_combine(base3, 27, tot);
+    lob_stamp(p, 8);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 18; ++i) H[i] = tot[i];
         // Gram of the twice-projected block: the second correction is O(eps) so
@@ -300,6 +318,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
         blk_times(w, T, 3, wn);
         st9(p.W + o, wn);
     }
+    lob_stamp(p, 9);
 }
 
 inline int lobpcg_grid(int n_c) {

@@ -36,7 +36,13 @@ struct PeerCtrl {            // lives at the start of every window
     unsigned int timeouts;                // waits that gave up (a peer never arrived): results are invalid
     unsigned int pad;
     unsigned long long dirty[2];          // doubles of buffer 0 / 1 that are not zero (set by the call that used it)
+    unsigned long long stamp[4];          // globaltimer (ns) of the last call: publish, flags seen (CTA 0), sums done (CTA 0), end
 };
+__device__ __forceinline__ unsigned long long peer_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 constexpr long long PEER_SPIN_LIMIT = 20000000000ll;   // clock64 ticks (~10 s): a lost peer becomes an error, not a hung GPU
 constexpr size_t PEER_CTRL_BYTES = 256;   // >= sizeof(PeerCtrl), keeps the buffers 256-byte aligned
 
@@ -64,6 +70,10 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// __threadfence() / __threadfence_system() are fence.sc (MEMBAR.SC: totally ordered, expensive when
+// hundreds of CTAs issue them together); release / acquire patterns only need fence.acq_rel
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ double2 ld_peer2(const double* p) {
     double2 v;
     asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
@@ -75,14 +85,15 @@ __device__ __forceinline__ double2 ld_peer2(const double* p) {
 __device__ __forceinline__ void peer_publish(const PeerDev& pd, unsigned long long epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();   // cumulative: covers the whole CTA's writes (ordered before this thread by the barrier)
+        fence_acq_rel_gpu();   // cumulative: covers the whole CTA's writes (ordered before this thread by the barrier)
         PeerCtrl* me = pd.ctrl[pd.rank];
         const unsigned int old = atomicAdd(&me->done, 1u);
         if (old == gridDim.x - 1) {
             // ONE system-scope fence orders every CTA's window writes (made visible to this thread through
             // the counter) before the flag stores; the stores themselves are relaxed and pipeline over NVLink
             // (a st.release per peer would serialise 8 fence + round-trip pairs)
-            __threadfence_system();
+            me->stamp[0] = peer_now();
+            fence_acq_rel_sys();
 #pragma unroll
             for (int r = 0; r < PEER_MAX; ++r)
                 if (r < pd.world) st_relaxed_sys(&pd.ctrl[r]->flags[pd.rank], epoch);
@@ -96,14 +107,16 @@ __device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long lon
     PeerCtrl* me = pd.ctrl[pd.rank];
     const int opar = (int)((epoch + 1ull) & 1ull);
     const long long dirty_other = (long long)me->dirty[opar];   // written by the previous call's last CTA
-    if (threadIdx.x < pd.world) {
-        const unsigned long long* f = &me->flags[threadIdx.x];
+    if (threadIdx.x == 0) {                     // one polling thread per CTA, with back-off
         const long long t0 = clock64();
-        while (ld_relaxed_sys(f) < epoch) {
-            __nanosleep(64);
-            if (clock64() - t0 > PEER_SPIN_LIMIT) { atomicAdd(&me->timeouts, 1u); break; }
+        for (int r = 0; r < pd.world; ++r) {
+            while (ld_relaxed_sys(&me->flags[r]) < epoch) {
+                __nanosleep(200);
+                if (clock64() - t0 > PEER_SPIN_LIMIT) { atomicAdd(&me->timeouts, 1u); break; }
+            }
         }
-        __threadfence_system();   // acquire: the peers' window writes are ordered before their flags
+        fence_acq_rel_sys();                    // acquire: the peers' window writes are ordered before their flags
+        if (blockIdx.x == 0) me->stamp[1] = peer_now();
     }
     __syncthreads();
     const long long par = (long long)(epoch & 1ull) * pd.cap;
@@ -128,13 +141,15 @@ __device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long lon
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < dirty_other; i += stride) other[i] = 0.0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (blockIdx.x == 0) me->stamp[2] = peer_now();
+        fence_acq_rel_gpu();
         const unsigned int old = atomicAdd(&me->done2, 1u);
         if (old == gridDim.x - 1) {
             me->done = 0u; me->done2 = 0u;
             me->dirty[opar] = 0ull;
             me->dirty[opar ^ 1] = (unsigned long long)count;
-            __threadfence();
+            me->stamp[3] = peer_now();
+            fence_acq_rel_gpu();
             me->epoch = epoch;
         }
     }

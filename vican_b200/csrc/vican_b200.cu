@@ -437,6 +437,14 @@ int vb_peer_allreduce(void* ctx, double* buf, int64_t count, void* stream) {
 
 void* vb_peer_allreduce_fn(void) { return (void*)&vb_peer_allreduce; }
 
+int vb_peer_stamps(void* vctx, uint64_t* h_out4, void* stream) {
+    PeerCtx* ctx = (PeerCtx*)vctx;
+    if (!ctx) return VB_STATUS_BAD_ARGUMENT;
+    VB_CHECK(cudaMemcpyAsync(h_out4, ((PeerCtrl*)ctx->base)->stamp, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VB_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
 int vb_peer_status(void* vctx, void* stream) {
     PeerCtx* ctx = (PeerCtx*)vctx;
     if (!ctx) return VB_STATUS_BAD_ARGUMENT;
