@@ -23,7 +23,7 @@ def main():
     lib = _cabi.lib()
     comm = vdist.create_comm()
     assert comm.peer is not None
-    for n in (3, 3 * n_c + 8, 9 * n_c):
+    for n in (9 * n_c, 3, 3 * n_c + 8, 9 * n_c, 3):
         x = torch.randn(n, dtype=torch.float64, device="cuda")
         res = {}
         for name, fn in (("peer", lambda: lib.vb_peer_allreduce(comm.peer, _ptr(x), n, _stream())),

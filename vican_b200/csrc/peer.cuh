@@ -25,8 +25,8 @@
 namespace vb {
 
 constexpr int PEER_MAX = 8;
-constexpr int PEER_AR_THREADS = 256;
-constexpr int PEER_AR_CTAS = 64;
+constexpr int PEER_AR_THREADS = 512;
+constexpr int PEER_AR_CTAS = 128;
 
 struct PeerCtrl {            // lives at the start of every window
     unsigned long long flags[PEER_MAX];   // flags[r]: latest epoch rank r published (written by rank r)
