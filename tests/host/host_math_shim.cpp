@@ -24,7 +24,7 @@ void h_ritz9(const double* G, const double* M, const int* act, double* C, double
 }
 void h_ritz9_coop(const double* G, const double* M, const int* act, double* C, double* Cp, double* theta, int* actP) {
     double work[5 * 81 + 64];
-    int iwork[16];
+    int iwork[48];
     vb::ritz9_coop(G, M, act, C, Cp, theta, actP, work, iwork, 0, 1);
 }
 }

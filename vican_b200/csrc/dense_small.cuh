@@ -206,223 +206,242 @@ VB_HD void ritz9(const double* Gin, const double* Min, const int* act, double* C
 #define VB_SYNC() do { } while (0)
 #endif
 
-// round-robin tournament for 9 columns (+1 dummy): round r pairs, -1 = sits out
-VB_HD void rr_pair(int r, int m, int* p, int* q) {
-    // circle method on 10 players, player 9 fixed (dummy), others rotate
+// round-robin tournament (circle method) on np players, np even: in round r (0 <= r < np-1) pair m
+// (0 <= m < np/2) is (a, b); with an odd number of real columns the last player is a dummy and its
+// pair sits out (*p = -1)
+VB_HD void rr_pair(int np, int n_real, int r, int m, int* p, int* q) {
+    const int k = np - 1;
     int a, b;
-    if (m == 0) { a = 9; b = r % 9; }
-    else { a = (r + m) % 9; b = (r + 9 - m) % 9; }
-    if (a == 9 || b == 9) { *p = -1; *q = -1; return; }
+    if (m == 0) { a = k; b = r % k; }
+    else { a = (r + m) % k; b = (r + k - m) % k; }
+    if (a >= n_real || b >= n_real) { *p = -1; *q = -1; return; }
     if (a < b) { *p = a; *q = b; } else { *p = b; *q = a; }
 }
 
-// scratch: work >= 5*81 + 64 doubles ; iwork >= 16 ints
+// scratch: work >= 5*81 + 64 doubles ; iwork >= 48 ints
+//
+// Phases are loops over independent work items separated by VB_SYNC(); the design goal on the
+// device is a SHORT CHAIN of phases (the step kernel waits on this routine with the whole grid):
+//  * the problem is compacted to the active columns (3, 6 or 9 of them): 3 / 5 / 9 Jacobi rounds
+//    per sweep instead of always 9;
+//  * one Jacobi round = 2 phases: rotation parameters of the disjoint pairs, then the two-sided
+//    update G <- J^T G J and Q <- Q J written from the OLD matrices into a second buffer (no
+//    column-phase / row-phase / clean-up split);
+//  * the new search directions are M-orthonormalised by classical Gram-Schmidt applied twice with
+//    the products M [C Cp] cached, all dot products of a pass evaluated redundantly by every lane
+//    (7 phases per column instead of ~36).
 VB_HD void ritz9_coop(const double* Gin, const double* Min, const int* act, double* C, double* Cp, double* theta,
                       int* actP, double* work, int* iwork, int lane, int nl) {
-    double* G = work;            // 81
-    double* M = work + 81;       // 81
-    double* R = work + 162;      // 81 Cholesky factor
-    double* Ri = work + 243;     // 81 its inverse
-    double* Q = work + 324;      // 81 temp (G Ri), then eigenvectors
-    double* sc = work + 405;     // small scratch: [0..7] c,s of 4 pairs; [8] scale/floor; [9] dot; [10..18] MZ; [19..27] z; [28..36] lam
-    int* order = iwork;          // 9
-    int* flags = iwork + 9;      // [0] rotations in sweep
+    double* Ga = work;           // 81  G ping
+    double* Gb = work + 81;      // 81  G pong
+    double* Qa = work + 162;     // 81  Cholesky factor R, then Q ping
+    double* Ri = work + 243;     // 81  R^-1
+    double* Qb = work + 324;     // 81  temp (G Ri), partial maxima, then Q pong
+    double* sc = work + 405;     // 64: [0..8] ci, [9..17] si, [18..26] 1/R_jj, [27..35] order, [36..44] lam
+    int* a = iwork;              // [0..8]   active column list
+    int* part = iwork + 9;       // [9..17]  partner of a column in the current round
+    int* flags = iwork + 18;     // [18..20] "rotation seen in sweep s" in slot s % 3 (reset two sweeps ahead of its reuse)
+    int* pos = iwork + 21;       // [21..29] column -> compact position (-1 = inactive)
     const int n = 9;
-    for (int idx = lane; idx < 81; idx += nl) {
-        const int i = idx / n, j = idx - n * i;
-        const bool on = act[i] && act[j];
-        double g = on ? 0.5 * (Gin[i * n + j] + Gin[j * n + i]) : 0.0;
-        double m = on ? 0.5 * (Min[i * n + j] + Min[j * n + i]) : 0.0;
-        if (i == j && !act[i]) { m = 1.0; g = VB_BIG; }
-        G[idx] = g; M[idx] = m; R[idx] = 0.0; Ri[idx] = 0.0;
+    // ---- compact list of the active columns (every lane computes the same small table)
+    int na = 0;
+    for (int i = 0; i < n; ++i) na += act[i] ? 1 : 0;
+    if (lane == 0) {
+        int k = 0;
+        for (int i = 0; i < n; ++i) { pos[i] = act[i] ? k : -1; if (act[i]) a[k++] = i; }
+        flags[0] = 0; flags[1] = 0; flags[2] = 0;
     }
     VB_SYNC();
-    // Cholesky M = R^T R (upper R)
-    for (int j = 0; j < n; ++j) {
+    // compact symmetric copies: Ga = G, Gb = M (temporarily)
+    for (int idx = lane; idx < na * na; idx += nl) {
+        const int i = idx / na, j = idx - na * i;
+        const int gi = a[i], gj = a[j];
+        Ga[i * n + j] = 0.5 * (Gin[gi * n + gj] + Gin[gj * n + gi]);
+        Gb[i * n + j] = 0.5 * (Min[gi * n + gj] + Min[gj * n + gi]);
+        Qa[i * n + j] = 0.0; Ri[i * n + j] = 0.0;
+    }
+    VB_SYNC();
+    // ---- Cholesky M = R^T R (upper R in Qa), reciprocal pivots in sc[18..]
+    for (int j = 0; j < na; ++j) {
         if (lane == 0) {
-            double s = M[j * n + j];
-            for (int k = 0; k < j; ++k) s -= R[k * n + j] * R[k * n + j];
-            R[j * n + j] = sqrt(fmax(s, 1e-300));
+            double s = Gb[j * n + j];
+            for (int k = 0; k < j; ++k) s -= Qa[k * n + j] * Qa[k * n + j];
+            s = fmax(s, 1e-300);
+            const double r = sqrt(s);
+            Qa[j * n + j] = r;
+            sc[18 + j] = 1.0 / r;
         }
         VB_SYNC();
-        for (int i = j + 1 + lane; i < n; i += nl) {
-            double v = M[j * n + i];
-            for (int k = 0; k < j; ++k) v -= R[k * n + j] * R[k * n + i];
-            R[j * n + i] = v / R[j * n + j];
+        for (int i = j + 1 + lane; i < na; i += nl) {
+            double v = Gb[j * n + i];
+            for (int k = 0; k < j; ++k) v -= Qa[k * n + j] * Qa[k * n + i];
+            Qa[j * n + i] = v * sc[18 + j];
         }
         VB_SYNC();
     }
     // Ri = R^-1 (upper): one column per work item
-    for (int j = lane; j < n; j += nl) {
-        Ri[j * n + j] = 1.0 / R[j * n + j];
+    for (int j = lane; j < na; j += nl) {
+        Ri[j * n + j] = sc[18 + j];
         for (int i = j - 1; i >= 0; --i) {
             double s = 0.0;
-            for (int k = i + 1; k <= j; ++k) s += R[i * n + k] * Ri[k * n + j];
-            Ri[i * n + j] = -s / R[i * n + i];
+            for (int k = i + 1; k <= j; ++k) s += Qa[i * n + k] * Ri[k * n + j];
+            Ri[i * n + j] = -s * sc[18 + i];
         }
     }
     VB_SYNC();
-    // Q = G Ri ; G = Ri^T Q ; symmetrise
-    for (int idx = lane; idx < 81; idx += nl) {
-        const int i = idx / n, j = idx - n * i;
+    // ---- whitened matrix A = Ri^T G Ri: Qb = G Ri, Gb = Ri^T Qb, then symmetrise into Ga, Qa = I
+    for (int idx = lane; idx < na * na; idx += nl) {
+        const int i = idx / na, j = idx - na * i;
         double s = 0.0;
-        for (int k = 0; k <= j; ++k) s += G[i * n + k] * Ri[k * n + j];
-        Q[idx] = s;
+        for (int k = 0; k <= j; ++k) s += Ga[i * n + k] * Ri[k * n + j];
+        Qb[i * n + j] = s;
     }
     VB_SYNC();
-    for (int idx = lane; idx < 81; idx += nl) {
-        const int i = idx / n, j = idx - n * i;
+    for (int idx = lane; idx < na * na; idx += nl) {
+        const int i = idx / na, j = idx - na * i;
         double s = 0.0;
-        for (int k = 0; k <= i; ++k) s += Ri[k * n + i] * Q[k * n + j];
-        G[idx] = s;
+        for (int k = 0; k <= i; ++k) s += Ri[k * n + i] * Qb[k * n + j];
+        Gb[i * n + j] = s;
     }
     VB_SYNC();
-    for (int idx = lane; idx < 81; idx += nl) {
-        const int i = idx / n, j = idx - n * i;
-        if (i < j) { const double s = 0.5 * (G[i * n + j] + G[j * n + i]); R[i * n + j] = s; R[j * n + i] = s; }
-        else if (i == j) R[idx] = G[idx];
-    }
-    VB_SYNC();
-    for (int idx = lane; idx < 81; idx += nl) {
-        const int i = idx / n, j = idx - n * i;
-        G[idx] = R[idx];
-        Q[idx] = (i == j) ? 1.0 : 0.0;
-    }
-    VB_SYNC();
-    // scale for the absolute "negligible" floor (masked columns carry VB_BIG and do not count)
-    if (lane == 0) {
-        double scale = 0.0;
-        for (int i = 0; i < 81; ++i) { const double v = fabs(G[i]); if (v < 1e-2 * VB_BIG && v > scale) scale = v; }
-        sc[8] = 1e-19 * scale + 1e-300;
-    }
-    VB_SYNC();
-    const double floor_abs = sc[8];
-    // parallel-ordered cyclic Jacobi
-    for (int sweep = 0; sweep < 40; ++sweep) {
-        if (lane == 0) flags[0] = 0;
-        VB_SYNC();
-        for (int r = 0; r < 9; ++r) {
-            for (int m = lane; m < 5; m += nl) {
-                int p, q;
-                rr_pair(r, m, &p, &q);
-                double c = 1.0, s = 0.0;
-                if (p >= 0) {
-                    const double apq = G[p * n + q], app = G[p * n + p], aqq = G[q * n + q];
-                    if (!(fabs(apq) <= floor_abs || fabs(apq) <= 1e-17 * sqrt(fabs(app) * fabs(aqq)))) {
-                        const double z = (aqq - app) / (2.0 * apq);
-                        const double t = (z >= 0.0 ? 1.0 : -1.0) / (fabs(z) + sqrt(1.0 + z * z));
-                        c = 1.0 / sqrt(1.0 + t * t);
-                        s = c * t;
-                        flags[1 + m] = 1;
-                    } else flags[1 + m] = 0;
-                } else flags[1 + m] = 0;
-                sc[2 * m] = c; sc[2 * m + 1] = s;
-            }
-            VB_SYNC();
-            // columns p,q of G and Q  (item = pair m, row i)
-            for (int idx = lane; idx < 5 * 9; idx += nl) {
-                const int m = idx / 9, i = idx - 9 * m;
-                int p, q;
-                rr_pair(r, m, &p, &q);
-                if (p < 0) continue;
-                const double c = sc[2 * m], s = sc[2 * m + 1];
-                const double gp = G[i * n + p], gq = G[i * n + q];
-                G[i * n + p] = c * gp - s * gq;
-                G[i * n + q] = s * gp + c * gq;
-                const double qp = Q[i * n + p], qq = Q[i * n + q];
-                Q[i * n + p] = c * qp - s * qq;
-                Q[i * n + q] = s * qp + c * qq;
-            }
-            VB_SYNC();
-            // rows p,q of G  (item = pair m, column j)
-            for (int idx = lane; idx < 5 * 9; idx += nl) {
-                const int m = idx / 9, j = idx - 9 * m;
-                int p, q;
-                rr_pair(r, m, &p, &q);
-                if (p < 0) continue;
-                const double c = sc[2 * m], s = sc[2 * m + 1];
-                const double gp = G[p * n + j], gq = G[q * n + j];
-                G[p * n + j] = c * gp - s * gq;
-                G[q * n + j] = s * gp + c * gq;
-            }
-            VB_SYNC();
-            for (int m = lane; m < 5; m += nl) {
-                int p, q;
-                rr_pair(r, m, &p, &q);
-                if (p >= 0) { G[p * n + q] = 0.0; G[q * n + p] = 0.0; if (flags[1 + m]) flags[0] = 1; }
-            }
-            VB_SYNC();
+    {
+        double mx = 0.0;
+        for (int idx = lane; idx < na * na; idx += nl) {
+            const int i = idx / na, j = idx - na * i;
+            const double v = 0.5 * (Gb[i * n + j] + Gb[j * n + i]);
+            Ga[i * n + j] = v;
+            Qa[i * n + j] = (i == j) ? 1.0 : 0.0;
+            mx = fmax(mx, fabs(v));
         }
-        if (flags[0] == 0) break;
+        Qb[81 - 32 + (lane & 31)] = mx;     // tail of Qb: its compact matrix part is not live here
     }
-    // sort ascending by rank counting
-    double* lam = sc + 28;
-    for (int i = lane; i < n; i += nl) lam[i] = G[i * n + i];
     VB_SYNC();
-    for (int i = lane; i < n; i += nl) {
+    double scale = 0.0;
+    for (int l = 0; l < nl && l < 32; ++l) scale = fmax(scale, Qb[81 - 32 + l]);
+    const double floor_abs = 1e-19 * scale + 1e-300;
+    // ---- parallel-ordered cyclic Jacobi on the na x na matrix
+    const int np = (na + 1) & ~1;            // players of the tournament (dummy added when na is odd)
+    const int rounds = np - 1, pairs = np / 2;
+    double *Gc = Ga, *Gn = Gb, *Qc = Qa, *Qn = Qb;
+    for (int sweep = 0; sweep < 40 && na > 1; ++sweep) {
+        for (int r = 0; r < rounds; ++r) {
+            // phase A: rotation of every pair of the round -> per-column tables (partner, c, s)
+            for (int m = lane; m < pairs; m += nl) {
+                int p, q;
+                rr_pair(np, na, r, m, &p, &q);
+                if (m == 0) {
+                    if (r == 0) flags[(sweep + 1) % 3] = 0;               // next sweep's slot: last read two sweeps ago
+                    if (na & 1) { const int lone = r % rounds; part[lone] = lone; sc[lone] = 1.0; sc[9 + lone] = 0.0; }
+                }
+                if (p < 0) continue;
+                double c = 1.0, sn = 0.0;
+                const double apq = Gc[p * n + q], app = Gc[p * n + p], aqq = Gc[q * n + q];
+                if (!(fabs(apq) <= floor_abs || fabs(apq) <= 1e-17 * sqrt(fabs(app) * fabs(aqq)))) {
+                    const double z = (aqq - app) / (2.0 * apq);
+                    const double t = (z >= 0.0 ? 1.0 : -1.0) / (fabs(z) + sqrt(1.0 + z * z));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    sn = c * t;
+                    flags[sweep % 3] = 1;
+                }
+                // new column p = c col_p - s col_q ; new column q = s col_p + c col_q
+                part[p] = q; sc[p] = c; sc[9 + p] = -sn;
+                part[q] = p; sc[q] = c; sc[9 + q] = sn;
+            }
+            VB_SYNC();
+            // phase B: G' = J^T G J and Q' = Q J from the old matrices into the other buffers
+            for (int idx = lane; idx < na * na; idx += nl) {
+                const int i = idx / na, j = idx - na * i;
+                const int pi = part[i], pj = part[j];
+                const double ci = sc[i], si = sc[9 + i], cj = sc[j], sj = sc[9 + j];
+                const double g = ci * (cj * Gc[i * n + j] + sj * Gc[i * n + pj]) + si * (cj * Gc[pi * n + j] + sj * Gc[pi * n + pj]);
+                Gn[i * n + j] = (pi == j && i != j) ? 0.0 : g;          // the annihilated pair entries
+                Qn[i * n + j] = cj * Qc[i * n + j] + sj * Qc[i * n + pj];
+            }
+            VB_SYNC();
+            double* tg = Gc; Gc = Gn; Gn = tg;
+            double* tq = Qc; Qc = Qn; Qn = tq;
+        }
+        if (flags[sweep % 3] == 0) break;
+    }
+    // ---- eigenvalues ascending (rank counting), the 3 lowest Ritz vectors in the original basis
+    for (int i = lane; i < na; i += nl) {
+        const double li = Gc[i * n + i];
         int rank = 0;
-        for (int j = 0; j < n; ++j) rank += (lam[j] < lam[i]) || (lam[j] == lam[i] && j < i);
-        order[rank] = i;
+        for (int j = 0; j < na; ++j) { const double lj = Gc[j * n + j]; rank += (lj < li) || (lj == li && j < i); }
+        sc[27 + rank] = (double)i;
+        sc[36 + i] = li;
     }
     VB_SYNC();
     for (int idx = lane; idx < 27; idx += nl) {
-        const int i = idx / 3, j = idx - 3 * i;
-        const int col = order[j];
+        const int gi = idx / 3, j = idx - 3 * gi;
+        const int i = pos[gi];
         double s = 0.0;
-        for (int k = i; k < n; ++k) s += Ri[i * n + k] * Q[k * n + col];
+        if (i >= 0 && j < na) {
+            const int col = (int)sc[27 + j];
+            for (int k = i; k < na; ++k) s += Ri[i * n + k] * Qc[k * n + col];
+            if (i == 0) theta[j] = sc[36 + col];
+        }
         C[idx] = s;
-        if (i == 0) theta[j] = lam[col];
+        Cp[idx] = 0.0;
     }
+    if (lane == 0) for (int j = na; j < 3; ++j) theta[j] = VB_BIG;
     VB_SYNC();
-    // new search directions: Z = [0; C_w; C_p], M-orthogonalised against C and the accepted
-    // columns (modified Gram-Schmidt, twice), dropped when nothing is left
-    double* MZ = sc + 10;
-    double* z = sc + 19;
+    // ---- new search directions: Z = [0; C_w; C_p] M-orthonormalised against C and the accepted
+    // columns by classical Gram-Schmidt applied twice, dropped when nothing is left.
+    // MB[:, c] = M B[:, c] for B = [C | Cp] is cached (Ga: 9 x 6), z in Gb[0..8], M z in Gb[9..17].
+    double* MB = Ga;
+    double* z = Gb;
+    double* Mz = Gb + 9;
+    auto Msym = [&](int i, int k) { return 0.5 * (Min[i * n + k] + Min[k * n + i]); };
+    for (int idx = lane; idx < 27; idx += nl) {
+        const int i = idx / 3, c = idx - 3 * i;
+        double s = 0.0;
+        if (act[i]) for (int k = 0; k < n; ++k) if (act[k]) s += Msym(i, k) * C[k * 3 + c];
+        MB[i * 6 + c] = s;
+    }
     for (int j = 0; j < 3; ++j) {
         for (int i = lane; i < n; i += nl) z[i] = (i < 3) ? 0.0 : C[i * 3 + j];
         VB_SYNC();
+        for (int i = lane; i < n; i += nl) {
+            double s = 0.0;
+            if (act[i]) for (int k = 0; k < n; ++k) if (act[k]) s += Msym(i, k) * z[k];
+            Mz[i] = s;
+        }
+        VB_SYNC();
         double n0 = 0.0;
-        for (int pass = 0; pass < 3; ++pass) {       // pass 0: norm before; 1,2: projections
-            for (int cidx = 0; cidx < ((pass == 0) ? 1 : 3 + j); ++cidx) {
-                for (int i = lane; i < n; i += nl) {
-                    double s = 0.0;
-                    for (int k = 0; k < n; ++k) s += M[i * n + k] * z[k];
-                    MZ[i] = s;
-                }
-                VB_SYNC();
-                if (pass == 0) {
-                    if (lane == 0) { double s = 0.0; for (int i = 0; i < n; ++i) s += z[i] * MZ[i]; sc[9] = sqrt(fmax(s, 0.0)); }
-                    VB_SYNC();
-                    n0 = sc[9];
-                    continue;
-                }
-                const double* b = (cidx < 3) ? C : Cp;
-                const int bc = (cidx < 3) ? cidx : cidx - 3;
-                const bool use = (cidx < 3) || actP[bc];
-                if (lane == 0) { double s = 0.0; if (use) for (int i = 0; i < n; ++i) s += b[i * 3 + bc] * MZ[i]; sc[9] = s; }
-                VB_SYNC();
-                const double dot = sc[9];
-                for (int i = lane; i < n; i += nl) z[i] -= dot * b[i * 3 + bc];
-                VB_SYNC();
+        for (int i = 0; i < n; ++i) n0 += z[i] * Mz[i];
+        n0 = sqrt(fmax(n0, 0.0));
+        for (int pass = 0; pass < 2; ++pass) {
+            double d[5];
+            for (int c = 0; c < 3 + j; ++c) {
+                double s = 0.0;
+                if (c < 3 || actP[c - 3]) for (int i = 0; i < n; ++i) s += MB[i * 6 + c] * z[i];
+                d[c] = s;
             }
+            VB_SYNC();                       // every lane has read z before anybody updates it
+            for (int i = lane; i < n; i += nl) {
+                double v = z[i];
+                for (int c = 0; c < 3 + j; ++c) v -= d[c] * ((c < 3) ? C[i * 3 + c] : Cp[i * 3 + (c - 3)]);
+                z[i] = v;
+            }
+            VB_SYNC();
         }
         for (int i = lane; i < n; i += nl) {
             double s = 0.0;
-            for (int k = 0; k < n; ++k) s += M[i * n + k] * z[k];
-            MZ[i] = s;
+            if (act[i]) for (int k = 0; k < n; ++k) if (act[k]) s += Msym(i, k) * z[k];
+            Mz[i] = s;
         }
         VB_SYNC();
-        if (lane == 0) {
-            double s = 0.0;
-            for (int i = 0; i < n; ++i) s += z[i] * MZ[i];
-            const double nz = sqrt(fmax(s, 0.0));
-            const bool keep = (nz > 1e-8 * fmax(n0, 1e-300)) && (nz > 1e-150);
-            actP[j] = keep ? 1 : 0;
-            sc[9] = keep ? 1.0 / nz : 0.0;
+        double nz = 0.0;
+        for (int i = 0; i < n; ++i) nz += z[i] * Mz[i];
+        nz = sqrt(fmax(nz, 0.0));
+        const bool keep = (nz > 1e-8 * fmax(n0, 1e-300)) && (nz > 1e-150);
+        const double inz = keep ? 1.0 / nz : 0.0;
+        for (int i = lane; i < n; i += nl) {
+            Cp[i * 3 + j] = z[i] * inz;
+            MB[i * 6 + 3 + j] = Mz[i] * inz;
         }
-        VB_SYNC();
-        const double inz = sc[9];
-        for (int i = lane; i < n; i += nl) Cp[i * 3 + j] = z[i] * inz;
+        if (lane == 0) actP[j] = keep ? 1 : 0;
         VB_SYNC();
     }
 }

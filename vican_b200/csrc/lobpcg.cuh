@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     __shared__ double red_sm[8 * 27];
     __shared__ double tot[LOB_NRED];
     __shared__ double Gm[81], Mm[81], Cx[27], Cp[27], work[5 * 81 + 64];
-    __shared__ int iwork[16];
+    __shared__ int iwork[48];
     __shared__ double theta_s[3], H[18], T[9];
     __shared__ int act_s[9], actP_s[3], actW_s[3], conv_s;
 
