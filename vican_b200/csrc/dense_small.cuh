@@ -12,6 +12,33 @@ namespace vb {
 
 #define VB_BIG 1e30
 
+// 1/sqrt(x): the device intrinsic (MUFU.RSQ64H + Newton, ~1 ulp) is several times cheaper than a
+// sqrt followed by a division, and the Jacobi / Cholesky chains below are pure latency
+VB_HD double vb_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// Jacobi rotation (c, s) annihilating a_pq: tan = sgn(d) w / (|d| + sqrt(d^2 + w^2)) with
+// d = a_qq - a_pp, w = 2 a_pq (the smaller root, |tan| <= 1), c = 1/sqrt(1 + tan^2), s = c tan.
+// One reciprocal square root for the hypotenuse, one reciprocal, one more reciprocal square root.
+VB_HD void jacobi_cs(double app, double aqq, double apq, double* c, double* s) {
+    const double d = aqq - app, w = 2.0 * apq;
+    const double h2 = d * d + w * w;
+    const double r = h2 * vb_rsqrt(h2);
+    const double t = (d >= 0.0 ? w : -w) * (1.0 / (fabs(d) + r));
+    const double cc = vb_rsqrt(1.0 + t * t);
+    *c = cc;
+    *s = cc * t;
+}
+// "negligible" test without a square root: |a_pq| <= 1e-17 sqrt(|a_pp a_qq|)
+VB_HD bool jacobi_negligible(double app, double aqq, double apq, double floor_abs) {
+    return fabs(apq) <= floor_abs || apq * apq <= 1e-34 * fabs(app * aqq);
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (n <= 9).
 // A is destroyed (its diagonal holds the eigenvalues), Q gets the eigenvectors in
 // columns; then eigenpairs are sorted ascending into lam / Q.
@@ -32,14 +59,13 @@ VB_HD void jacobi_eig_sym(int n, double* A, double* Q, double* lam) {
             for (int q = p + 1; q < n; ++q) {
                 const double apq = A[p * n + q];
                 const double app = A[p * n + p], aqq = A[q * n + q];
-                if (fabs(apq) <= floor_abs || fabs(apq) <= 1e-17 * sqrt(fabs(app) * fabs(aqq))) {
+                if (jacobi_negligible(app, aqq, apq, floor_abs)) {
                     A[p * n + q] = A[q * n + p] = 0.0;
                     continue;
                 }
                 ++nrot;
-                const double z = (aqq - app) / (2.0 * apq);
-                const double t = (z >= 0.0 ? 1.0 : -1.0) / (fabs(z) + sqrt(1.0 + z * z));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                double c, s;
+                jacobi_cs(app, aqq, apq, &c, &s);
                 for (int k = 0; k < n; ++k) {  // columns p,q
                     const double akp = A[k * n + p], akq = A[k * n + q];
                     A[k * n + p] = c * akp - s * akq;
@@ -267,9 +293,9 @@ VB_HD void ritz9_coop(const double* Gin, const double* Min, const int* act, doub
             double s = Gb[j * n + j];
             for (int k = 0; k < j; ++k) s -= Qa[k * n + j] * Qa[k * n + j];
             s = fmax(s, 1e-300);
-            const double r = sqrt(s);
-            Qa[j * n + j] = r;
-            sc[18 + j] = 1.0 / r;
+            const double ri = vb_rsqrt(s);
+            Qa[j * n + j] = s * ri;
+            sc[18 + j] = ri;
         }
         VB_SYNC();
         for (int i = j + 1 + lane; i < na; i += nl) {
@@ -336,11 +362,8 @@ VB_HD void ritz9_coop(const double* Gin, const double* Min, const int* act, doub
                 if (p < 0) continue;
                 double c = 1.0, sn = 0.0;
                 const double apq = Gc[p * n + q], app = Gc[p * n + p], aqq = Gc[q * n + q];
-                if (!(fabs(apq) <= floor_abs || fabs(apq) <= 1e-17 * sqrt(fabs(app) * fabs(aqq)))) {
-                    const double z = (aqq - app) / (2.0 * apq);
-                    const double t = (z >= 0.0 ? 1.0 : -1.0) / (fabs(z) + sqrt(1.0 + z * z));
-                    c = 1.0 / sqrt(1.0 + t * t);
-                    sn = c * t;
+                if (!jacobi_negligible(app, aqq, apq, floor_abs)) {
+                    jacobi_cs(app, aqq, apq, &c, &sn);
                     flags[sweep % 3] = 1;
                 }
                 // new column p = c col_p - s col_q ; new column q = s col_p + c col_q
