@@ -23,9 +23,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints exactly ONE line on stdout.  Libraries write banners there (NCCL prints its version
+# at NCCL_DEBUG=VERSION and above), so file descriptor 1 is pointed at stderr for the whole run
+# and the JSON line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -149,7 +156,7 @@ def run_reference(args):
                        "maxiter": maxiter, "lsqr_solver": "conjugate_gradient"},
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -335,6 +342,9 @@ def main():
             "config": {"workload": args.workload, "n_cameras": n_c, "n_time_nodes": n_t_glob, "n_edges": edges_total,
                        "cams_per_node": d, "maxiter": maxiter, "lsqr_solver": "conjugate_gradient",
                        "parallelism": "edge-sharded by time-node range x%d" % world,
+                       "collective": (None if world == 1 else
+                                      "one-shot all-reduce over NVLink peer memory, fused into the camera pass"
+                                      if comm.peer is not None else "ncclAllReduce per camera pass"),
                        "l2_policy": "inputs (%.1f GB of edge blocks per pass) larger than L2" % (76e-9 * edges_total / world)},
             "solve_ms": ms_per_step, "loop_iter_per_s": maxiter / (float(np.mean(loop_ms)) * 1e-3),
             "phase_ms": {"ingest": mean("ingest"), "rotation": mean("rotation"), "translation": mean("translation")},
@@ -344,7 +354,7 @@ def main():
             "max_rot_err_vs_ground_truth_rad": gt_err,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,
         }
-        print(json.dumps(line))
+        emit(line)
     vdist.destroy_comm(comm)
     if world > 1:
         tdist.destroy_process_group()

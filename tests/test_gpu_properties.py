@@ -143,3 +143,35 @@ def test_everything_filtered_and_bad_arguments(cuda):
         return 1.0
     bipgo.bipartite_se3sync(edges, cons, nm, nm, lambda e: e["reprojected_err"] < 0.005, 2, "conjugate_gradient")
     assert len(seen) == 2 * sum(1 for v in edges.values() if v["reprojected_err"] < 0.005)
+
+
+@pytest.mark.parametrize("filtered,outliers,maxiter", [(True, 0.2, 500), (False, 0.1, 60)])
+def test_cfg5_convergence_stress_matches_oracle(cuda, filtered, outliers, maxiter):
+    """BASELINE config 5 (large_shop shape with outliers, maxiter = 500) at 3 % of its time nodes so that
+    the oracle's 500 dense eigen-solves finish in half a minute: the rotation stage after 500
+    primal-dual iterations (20 % outliers removed by edge_filter), and after 60 iterations with 10 %
+    outliers LEFT IN the graph, against the oracle on the same arrays.  The long run also exercises the
+    statistics arrays past their 64 recorded iterations and the warm-started eigen-iteration
+    (one L-apply per outer iteration once converged)."""
+    from vican_b200 import solver
+    g = syn.make_camera_network(seed=11, n_cams=200, n_times=300, n_markers=24, cams_per_t=20, marks_per_cam=10,
+                                cube=True, outlier_frac=outliers)
+    keep = g.reproj < 0.5 if filtered else np.ones(g.n_edges, bool)
+    uc, ci = np.unique(g.cam[keep], return_inverse=True)
+    ut, ti = np.unique(g.time[keep], return_inverse=True)
+    R, w, mk = g.R[keep], g.w[keep], g.marker[keep]
+    n_c, n_t = len(uc), len(ut)
+    blk = orc.fold_blocks(R, w, mk, g.marker_R, 0)
+    pc, pt, B, a = orc.aggregate_pairs(ci, ti, blk, w, n_t)
+    r_c, r_t = orc.so3sync(pc, pt, B, a, n_c, n_t, maxiter)
+    C_m = np.transpose(g.marker_R, (0, 2, 1)) @ g.marker_R[0]
+    G = solver.DeviceGraph(ci.astype(np.int32), ti.astype(np.int32), mk.astype(np.int32), R, w, 2.0 * w, C_m, n_c, n_t)
+    rot = solver.solve_rotations(G, maxiter)
+    assert rot.status == 0 and rot.stats.outer_done == maxiter
+    ec = geodesic_rad(rot.r_c.cpu().numpy(), r_c).max()
+    et = geodesic_rad(rot.r_t.cpu().numpy(), r_t).max()
+    assert ec <= 1e-8 and et <= 1e-8, (ec, et)
+    # converged regime: the eigen-iteration is warm started, so late outer iterations need a single L-apply
+    inner = list(rot.stats.inner_per_outer[:min(maxiter, 64)])
+    assert inner[-1] <= 2 and sum(inner[10:]) <= 2 * len(inner[10:]), inner
+    assert rot.stats.time_passes <= 2 * maxiter + sum(inner) + 40
