@@ -42,21 +42,49 @@ struct LobpcgParams {
     int first;
 };
 
-template <int N>
-__device__ __forceinline__ void block_reduce_store(double (&v)[N], double* sm /*[8][N]*/, double* dst) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ---- warp reduce-scatter: sums N per-lane values over the 32 lanes with a halving butterfly.
+// At the step with lane mask MASK every lane keeps one half of its live values and ships the other
+// half to its partner, so the whole reduction costs about N fp64 shuffles instead of 5 N (shuffles
+// share the LSU pipe with shared/global loads; a plain all-reduce of the 108 Gram entries was
+// the longest part of the vector stages).  After the last step a lane holds the totals of the values
+// [base, base + count) of the original array (entries beyond N are padding) and emits them.
+template <int N, int MASK>
+struct RsStep {
+    static constexpr int H = (N + 1) / 2;
+    template <typename F>
+    __device__ __forceinline__ static void run(const double (&v)[N], int lane, int base, F&& emit) {
+        const bool up = (lane & MASK) != 0;
+        double w[H];
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-    __syncthreads();
-    if (lane == 0) {
+        for (int m = 0; m < H; ++m) {
+            const double lo = v[m];
+            const double hi = (H + m < N) ? v[H + m] : 0.0;
+            const double recv = shfl_xor(up ? lo : hi, MASK);
+            w[m] = (up ? hi : lo) + recv;
+        }
+        const int nbase = base + (up ? H : 0);
+        if constexpr (MASK > 1) RsStep<H, MASK / 2>::run(w, lane, nbase, emit);
+        else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) sm[warp * N + i] = v[i];
+            for (int m = 0; m < H; ++m) emit(nbase + m, w[m]);
+        }
     }
+};
+
+// block-level sum of N per-thread values -> dst[0..N) (one slot per CTA, deterministic order):
+// reduce-scatter inside every warp, holders drop their totals into shared memory, N threads add the
+// per-warp rows.  `sm` must hold (LOB_THREADS / 32) * N doubles.  Ends with a __syncthreads().
+template <int N>
+__device__ __forceinline__ void block_sum_store(const double (&v)[N], double* sm, double* dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* row = sm + warp * N;
+    RsStep<N, 16>::run(v, lane, 0, [&](int idx, double tot) { if (idx < N) row[idx] = tot; });
     __syncthreads();
     if (threadIdx.x < N) {
-        double s = 0.0;
-        for (int w = 0; w < LOB_THREADS / 32; ++w) s += sm[w * N + threadIdx.x];
-        dst[threadIdx.x] = s;
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < LOB_THREADS / 32; ++w) t += sm[w * N + threadIdx.x];
+        dst[threadIdx.x] = t;
     }
     __syncthreads();
 }
@@ -71,29 +99,24 @@ __device__ __forceinline__ void grid_combine(const double* partial, int n, doubl
     __syncthreads();
 }
 
-__device__ __forceinline__ void ld9(const double* p, double* v) {
+__device__ __forceinline__ void ld3(const double* p, double* v) { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; }
+__device__ __forceinline__ void st3(double* p, const double* v) { p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; }
+// out[j] += sum_jj v[jj] * Cm[jj * 3 + j]     (row vector times 3x3)
+__device__ __forceinline__ void row_times(const double* v, const double* Cm, double* out) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) v[i] = p[i];
+    for (int j = 0; j < 3; ++j) out[j] += v[0] * Cm[j] + v[1] * Cm[3 + j] + v[2] * Cm[6 + j];
 }
-__device__ __forceinline__ void st9(double* p, const double* v) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) p[i] = v[i];
-}
-// acc[3j+jp] += sum_i a[3i+j] b[3i+jp]      (a^T b for row-major 3x3 blocks)
-__device__ __forceinline__ void atb_acc(const double* a, const double* b, double* acc) {
+// acc[3j+jp] += a[j] * b[jp]      (contribution of one row to a^T b)
+__device__ __forceinline__ void outer_acc(const double* a, const double* b, double* acc) {
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int jp = 0; jp < 3; ++jp)
-            acc[3 * j + jp] += a[j] * b[jp] + a[3 + j] * b[3 + jp] + a[6 + j] * b[6 + jp];
+        for (int jp = 0; jp < 3; ++jp) acc[3 * j + jp] += a[j] * b[jp];
 }
-// out[3i+j] (+)= sum_jj v[3i+jj] * Cm[(jj)*ldc + j]
-__device__ __forceinline__ void blk_times(const double* v, const double* Cm, int ldc, double* out) {
+// row i of (block-diagonal 3x3) * (3 rows of the camera): out[j] = sum_k l[k] * V[3 k + j]
+__device__ __forceinline__ void blockrow_times(const double* l, const double* V9, double* out) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            out[3 * i + j] += v[3 * i] * Cm[j] + v[3 * i + 1] * Cm[ldc + j] + v[3 * i + 2] * Cm[2 * ldc + j];
+    for (int j = 0; j < 3; ++j) out[j] = l[0] * V9[j] + l[1] * V9[3 + j] + l[2] * V9[6 + j];
 }
 
 __device__ __forceinline__ void lob_stamp(const LobpcgParams& p, int k) {
@@ -104,21 +127,30 @@ __device__ __forceinline__ void lob_stamp(const LobpcgParams& p, int k) {
     }
 }
 
+// Work decomposition: one thread per ROW of the block vectors (row r = 3 c + i of camera c; a
+// block vector [n_c][9] is a row-major [3 n_c][3] matrix, so consecutive threads read consecutive
+// 24-byte rows: coalesced, three times the parallelism of a thread per camera).  A CTA owns
+// LOB_ROWS = 255 rows per chunk = 85 whole cameras, so the two block-diagonal products
+// (Lambda_C V and Lambda_C^-1 R read the three rows of a camera) never cross a CTA.
+constexpr int LOB_ROWS = 255;
+
 __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParams p) {
     // a speculatively enqueued step after convergence is a no-op (uniform across the grid: the flag
     // was written by the previous launch)
     if (!p.first && p.small[SM_CONV] != 0.0) return;
     cg::grid_group grid = cg::this_grid();
-    __shared__ double red_sm[8 * 27];
+    __shared__ double red_sm[(LOB_THREADS / 32) * 27];
     __shared__ double tot[LOB_NRED];
     __shared__ double Gm[81], Mm[81], Cx[27], Cp[27], work[5 * 81 + 64];
     __shared__ int iwork[48];
     __shared__ double theta_s[3], H[18], T[9];
     __shared__ int act_s[9], actP_s[3], actW_s[3], conv_s;
 
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gthreads = gridDim.x * blockDim.x;
-    const int n_c = p.n_c;
+    const int n_rows = 3 * p.n_c;
+    const int row0 = blockIdx.x * LOB_ROWS + threadIdx.x;          // first row of this thread
+    const int rstride = gridDim.x * LOB_ROWS;
+    const bool rower = threadIdx.x < LOB_ROWS;                     // thread 255 only helps in the reductions
+    const int irow = threadIdx.x % 3;                              // row inside the camera block (LOB_ROWS % 3 == 0)
     const double* base1 = p.partial;
     const double* base2 = p.partial + (size_t)gridDim.x * LOB_NRED;
     const double* base3 = p.partial + (size_t)2 * gridDim.x * LOB_NRED;
@@ -131,37 +163,55 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     {
         double* V = p.first ? p.X : p.W;
         double* AV = p.first ? p.AX : p.AW;
-        double an[1] = {0.0};
-        for (int c = gtid; c < n_c; c += gthreads) {
-            double v[9], y[9], l[9], o[9];
-            ld9(V + 9 * (size_t)c, v);
-            ld9(p.Y + 9 * (size_t)c, y);
-            ld9(p.lamC + 9 * (size_t)c, l);
-            mm3(l, v, o);
+        double an = 0.0;
+        if (rower)
+            for (int r = row0; r < n_rows; r += rstride) {
+                double v[9], y[3], l[3], o[3];
+                const double* vc = V + 3 * (size_t)(r - irow);     // the camera's three rows
 #pragma unroll
-            for (int i = 0; i < 9; ++i) { o[i] -= y[i]; an[0] += l[i] * l[i]; }
-            st9(AV + 9 * (size_t)c, o);
-        }
-        block_reduce_store<1>(an, red_sm, part1 + 108);
-        // stores above are re-read below by the same thread only (same camera stride) -> no sync needed
+                for (int q = 0; q < 9; ++q) v[q] = vc[q];
+                ld3(p.Y + 3 * (size_t)r, y);
+                ld3(p.lamC + 3 * (size_t)r, l);
+                blockrow_times(l, v, o);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) o[j] -= y[j];
+                an += l[0] * l[0] + l[1] * l[1] + l[2] * l[2];
+                st3(AV + 3 * (size_t)r, o);
+            }
+        // the row stored above is re-read below by the same thread only -> no sync needed
         const double* Vs[3] = {p.X, p.W, p.P};
         const double* AVs[3] = {p.AX, p.AW, p.AP};
         int blk = 0;
         for (int a = 0; a < 3; ++a)
             for (int b = a; b < 3; ++b, ++blk) {
-                double g[9], m[9];
+                double gm[19];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) { g[i] = 0.0; m[i] = 0.0; }
-                for (int c = gtid; c < n_c; c += gthreads) {
-                    double va[9], vb_[9], avb[9];
-                    ld9(Vs[a] + 9 * (size_t)c, va);
-                    ld9(Vs[b] + 9 * (size_t)c, vb_);
-                    ld9(AVs[b] + 9 * (size_t)c, avb);
-                    atb_acc(va, avb, g);
-                    atb_acc(va, vb_, m);
+                for (int q = 0; q < 19; ++q) gm[q] = 0.0;
+                if (rower)
+                    for (int r = row0; r < n_rows; r += rstride) {
+                        double va[3], vb_[3], avb[3];
+                        ld3(Vs[a] + 3 * (size_t)r, va);
+                        ld3(Vs[b] + 3 * (size_t)r, vb_);
+                        ld3(AVs[b] + 3 * (size_t)r, avb);
+                        outer_acc(va, avb, gm);
+                        outer_acc(va, vb_, gm + 9);
+                    }
+                gm[18] = (blk == 0) ? an : 0.0;
+                // 19 totals of this block pair: G block -> part1[9 blk ..], M block -> part1[54 + 9 blk ..], |Lambda_C|^2 -> [108]
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                double* row = red_sm + warp * 19;
+                RsStep<19, 16>::run(gm, lane, 0, [&](int idx, double t) { if (idx < 19) row[idx] = t; });
+                __syncthreads();
+                if (threadIdx.x < 19) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int w = 0; w < LOB_THREADS / 32; ++w) t += red_sm[w * 19 + threadIdx.x];
+                    const int q = threadIdx.x;
+                    if (q < 9) part1[9 * blk + q] = t;
+                    else if (q < 18) part1[54 + 9 * blk + (q - 9)] = t;
+                    else if (blk == 0) part1[108] = t;
                 }
-                block_reduce_store<9>(g, red_sm, part1 + 9 * blk);
-                block_reduce_store<9>(m, red_sm, part1 + 54 + 9 * blk);
+                __syncthreads();
             }
     }
     lob_stamp(p, 1);
@@ -195,42 +245,50 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     lob_stamp(p, 4);
 
     // ---------------- stage 3: basis update, residual, preconditioned direction ------------
-    const double anorm = sqrt(tot[108] / (3.0 * n_c));
+    const double anorm = sqrt(tot[108] / (3.0 * p.n_c));
     {
+        // 3a (row-local, in place): X, P, AX, AP <- basis update; the residual row R = AX - X theta is parked in
+        // the AW array (A W is dead from here on; the next step recomputes it)
+        if (rower)
+            for (int r = row0; r < n_rows; r += rstride) {
+                const size_t o = 3 * (size_t)r;
+                double x[3], w[3], pp[3], xn[3] = {0, 0, 0}, pn[3] = {0, 0, 0};
+                ld3(p.X + o, x); ld3(p.W + o, w); ld3(p.P + o, pp);
+                row_times(x, Cx, xn);  row_times(w, Cx + 9, xn);  row_times(pp, Cx + 18, xn);
+                row_times(x, Cp, pn);  row_times(w, Cp + 9, pn);  row_times(pp, Cp + 18, pn);
+                st3(p.X + o, xn); st3(p.P + o, pn);
+                double ax[3], aw[3], ap[3], axn[3] = {0, 0, 0}, apn[3] = {0, 0, 0}, res[3];
+                ld3(p.AX + o, ax); ld3(p.AW + o, aw); ld3(p.AP + o, ap);
+                row_times(ax, Cx, axn);  row_times(aw, Cx + 9, axn);  row_times(ap, Cx + 18, axn);
+                row_times(ax, Cp, apn);  row_times(aw, Cp + 9, apn);  row_times(ap, Cp + 18, apn);
+                st3(p.AX + o, axn); st3(p.AP + o, apn);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) res[j] = axn[j] - xn[j] * theta_s[j];
+                st3(p.AW + o, res);
+            }
+        __syncthreads();   // the three rows of a camera live in one CTA
+        // 3b: W = Lambda_C^-1 R (block-Jacobi preconditioner), H = [X P]^T W, ||R_j||^2
         double acc[21];
 #pragma unroll
-        for (int i = 0; i < 21; ++i) acc[i] = 0.0;
-        for (int c = gtid; c < n_c; c += gthreads) {
-            const size_t o = 9 * (size_t)c;
-            double x[9], w[9], pp[9], xn[9], pn[9];
-            ld9(p.X + o, x); ld9(p.W + o, w); ld9(p.P + o, pp);
+        for (int q = 0; q < 21; ++q) acc[q] = 0.0;
+        if (rower)
+            for (int r = row0; r < n_rows; r += rstride) {
+                const size_t o = 3 * (size_t)r;
+                double R9[9], li[3], wn[3], xn[3], pn[3], rr[3];
+                const double* rc = p.AW + 3 * (size_t)(r - irow);
+                ld3(p.AW + o, rr);                                   // own residual row (no dynamic register indexing)
 #pragma unroll
-            for (int i = 0; i < 9; ++i) { xn[i] = 0.0; pn[i] = 0.0; }
-            blk_times(x, Cx, 3, xn);      blk_times(w, Cx + 9, 3, xn);  blk_times(pp, Cx + 18, 3, xn);
-            blk_times(x, Cp, 3, pn);      blk_times(w, Cp + 9, 3, pn);  blk_times(pp, Cp + 18, 3, pn);
-            st9(p.X + o, xn); st9(p.P + o, pn);
-            double ax[9], aw[9], ap[9], axn[9], apn[9];
-            ld9(p.AX + o, ax); ld9(p.AW + o, aw); ld9(p.AP + o, ap);
+                for (int q = 0; q < 9; ++q) R9[q] = rc[q];
+                ld3(p.lamCinv + o, li);
+                blockrow_times(li, R9, wn);
+                st3(p.W + o, wn);
+                ld3(p.X + o, xn); ld3(p.P + o, pn);
 #pragma unroll
-            for (int i = 0; i < 9; ++i) { axn[i] = 0.0; apn[i] = 0.0; }
-            blk_times(ax, Cx, 3, axn);    blk_times(aw, Cx + 9, 3, axn); blk_times(ap, Cx + 18, 3, axn);
-            blk_times(ax, Cp, 3, apn);    blk_times(aw, Cp + 9, 3, apn); blk_times(ap, Cp + 18, 3, apn);
-            st9(p.AX + o, axn); st9(p.AP + o, apn);
-            double r[9], li[9], wn[9];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    r[3 * i + j] = axn[3 * i + j] - xn[3 * i + j] * theta_s[j];
-                    acc[18 + j] += r[3 * i + j] * r[3 * i + j];
-                }
-            ld9(p.lamCinv + o, li);
-            mm3(li, r, wn);
-            st9(p.W + o, wn);
-            atb_acc(xn, wn, acc);
-            atb_acc(pn, wn, acc + 9);
-        }
-        block_reduce_store<21>(acc, red_sm, part2);
+                for (int j = 0; j < 3; ++j) acc[18 + j] += rr[j] * rr[j];
+                outer_acc(xn, wn, acc);
+                outer_acc(pn, wn, acc + 9);
+            }
+        block_sum_store<21>(acc, red_sm, part2);
     }
     lob_stamp(p, 5);
     grid.sync();
@@ -257,26 +315,25 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     {
         double acc[27];
 #pragma unroll
-        for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-        for (int c = gtid; c < n_c; c += gthreads) {
-            const size_t o = 9 * (size_t)c;
-            double x[9], pp[9], w[9];
-            ld9(p.X + o, x); ld9(p.P + o, pp); ld9(p.W + o, w);
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
+        for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+        if (rower)
+            for (int r = row0; r < n_rows; r += rstride) {
+                const size_t o = 3 * (size_t)r;
+                double x[3], pp[3], w[3];
+                ld3(p.X + o, x); ld3(p.P + o, pp); ld3(p.W + o, w);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    double s = 0.0;
+                    double sum = 0.0;
 #pragma unroll
-                    for (int jj = 0; jj < 3; ++jj) s += x[3 * i + jj] * H[3 * jj + j] + pp[3 * i + jj] * H[9 + 3 * jj + j];
-                    w[3 * i + j] -= s;
+                    for (int jj = 0; jj < 3; ++jj) sum += x[jj] * H[3 * jj + j] + pp[jj] * H[9 + 3 * jj + j];
+                    w[j] -= sum;
                 }
-            st9(p.W + o, w);
-            atb_acc(x, w, acc);
-            atb_acc(pp, w, acc + 9);
-            atb_acc(w, w, acc + 18);
-        }
-        block_reduce_store<27>(acc, red_sm, part3);
+                st3(p.W + o, w);
+                outer_acc(x, w, acc);
+                outer_acc(pp, w, acc + 9);
+                outer_acc(w, w, acc + 18);
+            }
+        block_sum_store<27>(acc, red_sm, part3);
     }
     lob_stamp(p, 7);
     grid.sync();
@@ -289,9 +346,9 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
         double Gw[9];
         for (int j = 0; j < 3; ++j)
             for (int jp = 0; jp < 3; ++jp) {
-                double s = tot[18 + 3 * j + jp];
-                for (int k = 0; k < 6; ++k) s -= tot[3 * k + j] * tot[3 * k + jp];
-                Gw[3 * j + jp] = s;
+                double sum = tot[18 + 3 * j + jp];
+                for (int k = 0; k < 6; ++k) sum -= tot[3 * k + j] * tot[3 * k + jp];
+                Gw[3 * j + jp] = sum;
             }
         svqb3(Gw, T, actW_s, 1e-12);
         if (blockIdx.x == 0)
@@ -300,29 +357,26 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     __syncthreads();
 
     // ---------------- stage 5: second projection + orthonormalisation ------------------------
-    for (int c = gtid; c < n_c; c += gthreads) {
-        const size_t o = 9 * (size_t)c;
-        double x[9], pp[9], w[9], wn[9];
-        ld9(p.X + o, x); ld9(p.P + o, pp); ld9(p.W + o, w);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
+    if (rower)
+        for (int r = row0; r < n_rows; r += rstride) {
+            const size_t o = 3 * (size_t)r;
+            double x[3], pp[3], w[3], wn[3] = {0, 0, 0};
+            ld3(p.X + o, x); ld3(p.P + o, pp); ld3(p.W + o, w);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                double s = 0.0;
+                double sum = 0.0;
 #pragma unroll
-                for (int jj = 0; jj < 3; ++jj) s += x[3 * i + jj] * H[3 * jj + j] + pp[3 * i + jj] * H[9 + 3 * jj + j];
-                w[3 * i + j] -= s;
+                for (int jj = 0; jj < 3; ++jj) sum += x[jj] * H[3 * jj + j] + pp[jj] * H[9 + 3 * jj + j];
+                w[j] -= sum;
             }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) wn[i] = 0.0;
-        blk_times(w, T, 3, wn);
-        st9(p.W + o, wn);
-    }
+            row_times(w, T, wn);
+            st3(p.W + o, wn);
+        }
     lob_stamp(p, 9);
 }
 
 inline int lobpcg_grid(int n_c) {
-    int want = (n_c + LOB_THREADS - 1) / LOB_THREADS;
+    int want = (3 * n_c + LOB_ROWS - 1) / LOB_ROWS;   // one thread per row, 255 rows (85 cameras) per CTA
     const int cap = sm_count();   // cooperative launch: all CTAs co-resident (1 CTA / SM)
     if (want < 1) want = 1;
     return want < cap ? want : cap;
