@@ -51,8 +51,10 @@ struct LobpcgParams {
 template <int N, int MASK>
 struct RsStep {
     static constexpr int H = (N + 1) / 2;
+    // `valid` = how many of the N entries are real (the upper half of an odd split carries one
+    // padding slot whose index belongs to the NEXT region: it must never be emitted)
     template <typename F>
-    __device__ __forceinline__ static void run(const double (&v)[N], int lane, int base, F&& emit) {
+    __device__ __forceinline__ static void run(const double (&v)[N], int lane, int base, int valid, F&& emit) {
         const bool up = (lane & MASK) != 0;
         double w[H];
 #pragma unroll
@@ -63,10 +65,12 @@ struct RsStep {
             w[m] = (up ? hi : lo) + recv;
         }
         const int nbase = base + (up ? H : 0);
-        if constexpr (MASK > 1) RsStep<H, MASK / 2>::run(w, lane, nbase, emit);
+        const int nvalid = up ? (valid > H ? valid - H : 0) : (valid < H ? valid : H);
+        if constexpr (MASK > 1) RsStep<H, MASK / 2>::run(w, lane, nbase, nvalid, emit);
         else {
 #pragma unroll
-            for (int m = 0; m < H; ++m) emit(nbase + m, w[m]);
+            for (int m = 0; m < H; ++m)
+                if (m < nvalid) emit(nbase + m, w[m]);
         }
     }
 };
@@ -78,7 +82,7 @@ template <int N>
 __device__ __forceinline__ void block_sum_store(const double (&v)[N], double* sm, double* dst) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* row = sm + warp * N;
-    RsStep<N, 16>::run(v, lane, 0, [&](int idx, double tot) { if (idx < N) row[idx] = tot; });
+    RsStep<N, 16>::run(v, lane, 0, N, [&](int idx, double tot) { row[idx] = tot; });
     __syncthreads();
     if (threadIdx.x < N) {
         double t = 0.0;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
                 // 19 totals of this block pair: G block -> part1[9 blk ..], M block -> part1[54 + 9 blk ..], |Lambda_C|^2 -> [108]
                 const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
                 double* row = red_sm + warp * 19;
-                RsStep<19, 16>::run(gm, lane, 0, [&](int idx, double t) { if (idx < 19) row[idx] = t; });
+                RsStep<19, 16>::run(gm, lane, 0, 19, [&](int idx, double t) { row[idx] = t; });
                 __syncthreads();
                 if (threadIdx.x < 19) {
                     double t = 0.0;
