@@ -102,17 +102,21 @@ VB_HD void jacobi_eig_sym(int n, double* A, double* Q, double* lam) {
 // returns T (3x3) such that (W T) has orthonormal columns; directions whose scaled
 // Gram eigenvalue is below drop_tol * max are dropped (T column = 0, act = 0).
 VB_HD void svqb3(const double* Gw, double* T, int* act, double drop_tol) {
-    double d[3], Gs[9], Q[9], lam[3];
-    for (int i = 0; i < 3; ++i) d[i] = sqrt(fmax(Gw[4 * i], 1e-300));
+    // The scaled Gram matrix is symmetric positive semi-definite, so its eigen-decomposition is its SVD:
+    // the register-resident one-sided Jacobi of mat3.cuh (compile-time indices) replaces the generic
+    // n x n Jacobi, whose run-time indexed local arrays cost ~8 us on one thread of the step kernel.
+    // Eigenvalues come out descending (lam[0] largest); the column order of T is irrelevant to the caller.
+    double d[3], Gs[9], U[9], Q[9], lam[3];
+    for (int i = 0; i < 3; ++i) d[i] = vb_rsqrt(fmax(Gw[4 * i], 1e-300));
     for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) Gs[3 * i + j] = 0.5 * (Gw[3 * i + j] + Gw[3 * j + i]) / (d[i] * d[j]);
-    jacobi_eig_sym(3, Gs, Q, lam);
-    const double lmax = fmax(lam[2], 1e-300);
+        for (int j = 0; j < 3; ++j) Gs[3 * i + j] = 0.5 * (Gw[3 * i + j] + Gw[3 * j + i]) * (d[i] * d[j]);
+    svd3(Gs, U, lam, Q);
+    const double lmax = fmax(lam[0], 1e-300);
     for (int j = 0; j < 3; ++j) {
         const bool keep = lam[j] > drop_tol * lmax;
         act[j] = keep ? 1 : 0;
-        const double sc = keep ? 1.0 / sqrt(lam[j]) : 0.0;
-        for (int i = 0; i < 3; ++i) T[3 * i + j] = Q[3 * i + j] / d[i] * sc;
+        const double sc = keep ? vb_rsqrt(lam[j]) : 0.0;
+        for (int i = 0; i < 3; ++i) T[3 * i + j] = Q[3 * i + j] * d[i] * sc;
     }
 }
 
@@ -384,6 +388,7 @@ VB_HD void ritz9_coop(const double* Gin, const double* Min, const int* act, doub
             double* tg = Gc; Gc = Gn; Gn = tg;
             double* tq = Qc; Qc = Qn; Qn = tq;
         }
+        if (lane == 0) iwork[30] = sweep + 1;      // diagnostics: sweeps used
         if (flags[sweep % 3] == 0) break;
     }
     // ---- eigenvalues ascending (rank counting), the 3 lowest Ritz vectors in the original basis

@@ -93,12 +93,15 @@ __device__ __forceinline__ void block_sum_store(const double (&v)[N], double* sm
     __syncthreads();
 }
 
-// deterministic: every CTA sums the per-CTA partials in the same order
+// deterministic: every CTA sums the per-CTA partials with the same tree (one warp per value: lanes
+// stride over the CTAs, xor butterfly), so all CTAs see bitwise identical totals
 __device__ __forceinline__ void grid_combine(const double* partial, int n, double* out_sm) {
-    if ((int)threadIdx.x < n) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = warp; q < n; q += LOB_THREADS / 32) {
         double s = 0.0;
-        for (int b = 0; b < (int)gridDim.x; ++b) s += partial[(size_t)b * LOB_NRED + threadIdx.x];
-        out_sm[threadIdx.x] = s;
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += partial[(size_t)b * LOB_NRED + q];
+        s = warp_sum(s);
+        if (lane == 0) out_sm[q] = s;
     }
     __syncthreads();
 }
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
         for (int i = lane; i < 9; i += 32) act_s[i] = (i < 3) ? 1 : (p.first ? 0 : (p.small[SM_ACT + i] != 0.0));
         __syncwarp();
         ritz9_coop(Gm, Mm, act_s, Cx, Cp, theta_s, actP_s, work, iwork, lane, 32);
+        if (lane == 0 && blockIdx.x == 0) p.small[SM_TIME + 10] = (double)iwork[30];   // Jacobi sweeps (diagnostics)
     }
     __syncthreads();
     lob_stamp(p, 4);

@@ -293,12 +293,12 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
             VB_CHECK(cudaEventSynchronize(ps.ev[slot]));
             hs = ps.h + slot * SM_SIZE;
             if (lob_timing) {
-                fprintf(stderr, "[lobpcg] outer %d step %d conv %.0f: stage1 %.1f sync1 %.1f combine %.1f ritz %.1f stage3 %.1f sync2+c %.1f stage4 %.1f sync3+c %.1f stage5 %.1f total %.1f us\n",
+                fprintf(stderr, "[lobpcg] outer %d step %d conv %.0f: stage1 %.1f sync1 %.1f combine %.1f ritz %.1f stage3 %.1f sync2+c %.1f stage4 %.1f sync3+c %.1f stage5 %.1f total %.1f us, %.0f Jacobi sweeps\n",
                         outer, inner, hs[SM_CONV], 1e-3 * (hs[SM_TIME + 1] - hs[SM_TIME]), 1e-3 * (hs[SM_TIME + 2] - hs[SM_TIME + 1]),
                         1e-3 * (hs[SM_TIME + 3] - hs[SM_TIME + 2]), 1e-3 * (hs[SM_TIME + 4] - hs[SM_TIME + 3]),
                         1e-3 * (hs[SM_TIME + 5] - hs[SM_TIME + 4]), 1e-3 * (hs[SM_TIME + 6] - hs[SM_TIME + 5]),
                         1e-3 * (hs[SM_TIME + 7] - hs[SM_TIME + 6]), 1e-3 * (hs[SM_TIME + 8] - hs[SM_TIME + 7]),
-                        1e-3 * (hs[SM_TIME + 9] - hs[SM_TIME + 8]), 1e-3 * (hs[SM_TIME + 9] - hs[SM_TIME]));
+                        1e-3 * (hs[SM_TIME + 9] - hs[SM_TIME + 8]), 1e-3 * (hs[SM_TIME + 9] - hs[SM_TIME]), hs[SM_TIME + 10]);
             }
             if (hs[SM_CONV] != 0.0) {
                 if (speculated) {
