@@ -102,16 +102,14 @@ VB_HD void jacobi_eig_sym(int n, double* A, double* Q, double* lam) {
 // returns T (3x3) such that (W T) has orthonormal columns; directions whose scaled
 // Gram eigenvalue is below drop_tol * max are dropped (T column = 0, act = 0).
 VB_HD void svqb3(const double* Gw, double* T, int* act, double drop_tol) {
-    // The scaled Gram matrix is symmetric positive semi-definite, so its eigen-decomposition is its SVD:
-    // the register-resident one-sided Jacobi of mat3.cuh (compile-time indices) replaces the generic
-    // n x n Jacobi, whose run-time indexed local arrays cost ~8 us on one thread of the step kernel.
-    // Eigenvalues come out descending (lam[0] largest); the column order of T is irrelevant to the caller.
-    double d[3], Gs[9], U[9], Q[9], lam[3];
+    // (the register-resident one-sided Jacobi SVD of mat3.cuh was tried here: it needs many more sweeps on a
+    // Gram matrix with a 1e-12 eigenvalue spread and measured 2-4x slower than the generic two-sided Jacobi)
+    double d[3], Gs[9], Q[9], lam[3];
     for (int i = 0; i < 3; ++i) d[i] = vb_rsqrt(fmax(Gw[4 * i], 1e-300));
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) Gs[3 * i + j] = 0.5 * (Gw[3 * i + j] + Gw[3 * j + i]) * (d[i] * d[j]);
-    svd3(Gs, U, lam, Q);
-    const double lmax = fmax(lam[0], 1e-300);
+    jacobi_eig_sym(3, Gs, Q, lam);
+    const double lmax = fmax(lam[2], 1e-300);
     for (int j = 0; j < 3; ++j) {
         const bool keep = lam[j] > drop_tol * lmax;
         act[j] = keep ? 1 : 0;
@@ -248,6 +246,58 @@ VB_HD void rr_pair(int np, int n_real, int r, int m, int* p, int* q) {
     if (a < b) { *p = a; *q = b; } else { *p = b; *q = a; }
 }
 
+// Parallel-ordered cyclic Jacobi sweeps on a compact NA x NA symmetric matrix (row stride 9) with
+// eigenvector accumulation, double buffered: Ga/Qa hold the input, the result is in *Gout / *Qout.
+// One round = 2 phases: (A) rotation parameters of the disjoint pairs -> per-column tables
+// (partner, c, s); (B) G' = J^T G J and Q' = Q J written from the old matrices into the other
+// buffers.  flags[3]: "rotation seen in sweep s" in slot s % 3.  Returns the sweeps used.
+template <int NA>
+VB_HD int jacobi_rounds(double* Ga, double* Gb, double* Qa, double* Qb, double* sc, int* part, int* flags,
+                        double floor_abs, int lane, int nl, double** Gout, double** Qout) {
+    constexpr int n = 9;
+    constexpr int NP = (NA + 1) & ~1;          // players of the tournament (dummy added when NA is odd)
+    constexpr int ROUNDS = NP - 1, PAIRS = NP / 2;
+    double *Gc = Ga, *Gn = Gb, *Qc = Qa, *Qn = Qb;
+    int sweep = 0;
+    for (; sweep < 40; ++sweep) {
+        for (int r = 0; r < ROUNDS; ++r) {
+            for (int m = lane; m < PAIRS; m += nl) {
+                int p, q;
+                rr_pair(NP, NA, r, m, &p, &q);
+                if (m == 0) {
+                    if (r == 0) flags[(sweep + 1) % 3] = 0;               // next sweep's slot: last read two sweeps ago
+                    if (NA & 1) { const int lone = r % ROUNDS; part[lone] = lone; sc[lone] = 1.0; sc[9 + lone] = 0.0; }
+                }
+                if (p < 0) continue;
+                double c = 1.0, sn = 0.0;
+                const double apq = Gc[p * n + q], app = Gc[p * n + p], aqq = Gc[q * n + q];
+                if (!jacobi_negligible(app, aqq, apq, floor_abs)) {
+                    jacobi_cs(app, aqq, apq, &c, &sn);
+                    flags[sweep % 3] = 1;
+                }
+                // new column p = c col_p - s col_q ; new column q = s col_p + c col_q
+                part[p] = q; sc[p] = c; sc[9 + p] = -sn;
+                part[q] = p; sc[q] = c; sc[9 + q] = sn;
+            }
+            VB_SYNC();
+            for (int idx = lane; idx < NA * NA; idx += nl) {
+                const int i = idx / NA, j = idx - NA * i;
+                const int pi = part[i], pj = part[j];
+                const double ci = sc[i], si = sc[9 + i], cj = sc[j], sj = sc[9 + j];
+                const double g = ci * (cj * Gc[i * n + j] + sj * Gc[i * n + pj]) + si * (cj * Gc[pi * n + j] + sj * Gc[pi * n + pj]);
+                Gn[i * n + j] = (pi == j && i != j) ? 0.0 : g;          // the annihilated pair entries
+                Qn[i * n + j] = cj * Qc[i * n + j] + sj * Qc[i * n + pj];
+            }
+            VB_SYNC();
+            double* tg = Gc; Gc = Gn; Gn = tg;
+            double* tq = Qc; Qc = Qn; Qn = tq;
+        }
+        if (flags[sweep % 3] == 0) { ++sweep; break; }
+    }
+    *Gout = Gc; *Qout = Qc;
+    return sweep;
+}
+
 // scratch: work >= 5*81 + 64 doubles ; iwork >= 48 ints
 //
 // Phases are loops over independent work items separated by VB_SYNC(); the design goal on the
@@ -349,48 +399,22 @@ VB_HD void ritz9_coop(const double* Gin, const double* Min, const int* act, doub
     double scale = 0.0;
     for (int l = 0; l < nl && l < 32; ++l) scale = fmax(scale, Qb[81 - 32 + l]);
     const double floor_abs = 1e-19 * scale + 1e-300;
-    // ---- parallel-ordered cyclic Jacobi on the na x na matrix
-    const int np = (na + 1) & ~1;            // players of the tournament (dummy added when na is odd)
-    const int rounds = np - 1, pairs = np / 2;
-    double *Gc = Ga, *Gn = Gb, *Qc = Qa, *Qn = Qb;
-    for (int sweep = 0; sweep < 40 && na > 1; ++sweep) {
-        for (int r = 0; r < rounds; ++r) {
-            // phase A: rotation of every pair of the round -> per-column tables (partner, c, s)
-            for (int m = lane; m < pairs; m += nl) {
-                int p, q;
-                rr_pair(np, na, r, m, &p, &q);
-                if (m == 0) {
-                    if (r == 0) flags[(sweep + 1) % 3] = 0;               // next sweep's slot: last read two sweeps ago
-                    if (na & 1) { const int lone = r % rounds; part[lone] = lone; sc[lone] = 1.0; sc[9 + lone] = 0.0; }
-                }
-                if (p < 0) continue;
-                double c = 1.0, sn = 0.0;
-                const double apq = Gc[p * n + q], app = Gc[p * n + p], aqq = Gc[q * n + q];
-                if (!jacobi_negligible(app, aqq, apq, floor_abs)) {
-                    jacobi_cs(app, aqq, apq, &c, &sn);
-                    flags[sweep % 3] = 1;
-                }
-                // new column p = c col_p - s col_q ; new column q = s col_p + c col_q
-                part[p] = q; sc[p] = c; sc[9 + p] = -sn;
-                part[q] = p; sc[q] = c; sc[9 + q] = sn;
-            }
-            VB_SYNC();
-            // phase B: G' = J^T G J and Q' = Q J from the old matrices into the other buffers
-            for (int idx = lane; idx < na * na; idx += nl) {
-                const int i = idx / na, j = idx - na * i;
-                const int pi = part[i], pj = part[j];
-                const double ci = sc[i], si = sc[9 + i], cj = sc[j], sj = sc[9 + j];
-                const double g = ci * (cj * Gc[i * n + j] + sj * Gc[i * n + pj]) + si * (cj * Gc[pi * n + j] + sj * Gc[pi * n + pj]);
-                Gn[i * n + j] = (pi == j && i != j) ? 0.0 : g;          // the annihilated pair entries
-                Qn[i * n + j] = cj * Qc[i * n + j] + sj * Qc[i * n + pj];
-            }
-            VB_SYNC();
-            double* tg = Gc; Gc = Gn; Gn = tg;
-            double* tq = Qc; Qc = Qn; Qn = tq;
-        }
-        if (lane == 0) iwork[30] = sweep + 1;      // diagnostics: sweeps used
-        if (flags[sweep % 3] == 0) break;
+    // ---- parallel-ordered cyclic Jacobi on the na x na matrix (size-specialised: the index arithmetic of
+    // the rounds is compile-time, a run-time `idx / na` per work item doubled the cost of a round)
+    double *Gc = Ga, *Qc = Qa;
+    int sweeps_used = 0;
+    switch (na) {
+        case 3: sweeps_used = jacobi_rounds<3>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
+        case 6: sweeps_used = jacobi_rounds<6>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
+        case 9: sweeps_used = jacobi_rounds<9>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
+        case 1: break;
+        case 2: sweeps_used = jacobi_rounds<2>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
+        case 4: sweeps_used = jacobi_rounds<4>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
+        case 5: sweeps_used = jacobi_rounds<5>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
+        case 7: sweeps_used = jacobi_rounds<7>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
+        default: sweeps_used = jacobi_rounds<8>(Ga, Gb, Qa, Qb, sc, part, flags, floor_abs, lane, nl, &Gc, &Qc); break;
     }
+    if (lane == 0) iwork[30] = sweeps_used;        // diagnostics
     // ---- eigenvalues ascending (rank counting), the 3 lowest Ritz vectors in the original basis
     for (int i = lane; i < na; i += nl) {
         const double li = Gc[i * n + i];

@@ -93,15 +93,28 @@ __device__ __forceinline__ void block_sum_store(const double (&v)[N], double* sm
     __syncthreads();
 }
 
-// deterministic: every CTA sums the per-CTA partials with the same tree (one warp per value: lanes
-// stride over the CTAs, xor butterfly), so all CTAs see bitwise identical totals
-__device__ __forceinline__ void grid_combine(const double* partial, int n, double* out_sm) {
+// deterministic: every CTA sums the per-CTA partials in the same order.  Lanes run along the value
+// index (coalesced rows of the partial table; a lane-per-CTA layout reads one 32-byte sector per
+// double and was 4x slower), the 8 warps split the CTAs, shared memory joins the 8 strands.
+__device__ __forceinline__ void grid_combine(const double* partial, int n, double* out_sm, double* comb_sm /*[8][LOB_NRED]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = warp; q < n; q += LOB_THREADS / 32) {
-        double s = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) s += partial[(size_t)b * LOB_NRED + q];
-        s = warp_sum(s);
-        if (lane == 0) out_sm[q] = s;
+    constexpr int NW = LOB_THREADS / 32;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = warp; b < (int)gridDim.x; b += NW) {
+        const double* row = partial + (size_t)b * LOB_NRED;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lane + 32 * u < n) s[u] += row[lane + 32 * u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < n) comb_sm[warp * LOB_NRED + lane + 32 * u] = s[u];
+    __syncthreads();
+    if ((int)threadIdx.x < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += comb_sm[w * LOB_NRED + threadIdx.x];
+        out_sm[threadIdx.x] = t;
     }
     __syncthreads();
 }
@@ -148,6 +161,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     cg::grid_group grid = cg::this_grid();
     __shared__ double red_sm[(LOB_THREADS / 32) * 27];
     __shared__ double tot[LOB_NRED];
+    __shared__ double comb_sm[(LOB_THREADS / 32) * LOB_NRED];
     __shared__ double Gm[81], Mm[81], Cx[27], Cp[27], work[5 * 81 + 64];
     __shared__ int iwork[48];
     __shared__ double theta_s[3], H[18], T[9];
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     lob_stamp(p, 1);
     grid.sync();
     lob_stamp(p, 2);
-    grid_combine(base1, 109, tot);
+    grid_combine(base1, 109, tot, comb_sm);
     lob_stamp(p, 3);
 
     // ---------------- stage 2: Rayleigh-Ritz (redundant per CTA, deterministic) ------------
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     }
     lob_stamp(p, 5);
     grid.sync();
-    grid_combine(base2, 21, tot);
+    grid_combine(base2, 21, tot, comb_sm);
     lob_stamp(p, 6);
     if (threadIdx.x == 0) {
         const double r0 = sqrt(tot[18]), r1 = sqrt(tot[19]), r2 = sqrt(tot[20]);
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
     }
     lob_stamp(p, 7);
     grid.sync();
-    grid_combine(base3, 27, tot);
+    grid_combine(base3, 27, tot, comb_sm);
     lob_stamp(p, 8);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 18; ++i) H[i] = tot[i];
