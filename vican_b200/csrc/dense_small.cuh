@@ -22,17 +22,17 @@ VB_HD double vb_rsqrt(double x) {
 #endif
 }
 
-// Jacobi rotation (c, s) annihilating a_pq: tan = sgn(d) w / (|d| + sqrt(d^2 + w^2)) with
-// d = a_qq - a_pp, w = 2 a_pq (the smaller root, |tan| <= 1), c = 1/sqrt(1 + tan^2), s = c tan.
-// One reciprocal square root for the hypotenuse, one reciprocal, one more reciprocal square root.
+// Jacobi rotation (c, s) annihilating a_pq, the smaller of the two roots (|tan| <= 1): with
+// d = a_qq - a_pp, w = 2 a_pq, r = sqrt(d^2 + w^2):  cos(2 theta) = |d| / r,
+//   c = sqrt((1 + cos 2theta) / 2),   s = sgn(d) w / (2 r c)      (= c tan, tan = sgn(d) w / (|d| + r)).
+// Two dependent reciprocal square roots and no division: the chain of the serial part of a round.
 VB_HD void jacobi_cs(double app, double aqq, double apq, double* c, double* s) {
     const double d = aqq - app, w = 2.0 * apq;
-    const double h2 = d * d + w * w;
-    const double r = h2 * vb_rsqrt(h2);
-    const double t = (d >= 0.0 ? w : -w) * (1.0 / (fabs(d) + r));
-    const double cc = vb_rsqrt(1.0 + t * t);
-    *c = cc;
-    *s = cc * t;
+    const double inv_r = vb_rsqrt(d * d + w * w);
+    const double x = 0.5 + 0.5 * (fabs(d) * inv_r);      // in [0.5, 1]
+    const double rs = vb_rsqrt(x);
+    *c = x * rs;
+    *s = (d >= 0.0 ? w : -w) * inv_r * (0.5 * rs);
 }
 // "negligible" test without a square root: |a_pq| <= 1e-17 sqrt(|a_pp a_qq|)
 VB_HD bool jacobi_negligible(double app, double aqq, double apq, double floor_abs) {
