@@ -37,7 +37,18 @@ __global__ void fill_identity_kernel(double* __restrict__ X, int64_t n) {
 
 // bipgo.py:295-297: r_c = project_SO3(V_c inv(V_0)); camera 0 is the gauge camera (first in the
 // reference's lexicographic node order -- the host assigns indices in that order).
-__global__ void __launch_bounds__(NODE_THREADS) gauge_project_kernel(const double* __restrict__ V, double* __restrict__ r_c, int64_t n_c) {
+// r12 (optional): the same blocks in the padded gather layout (3 rows x 4 doubles) for the next time pass
+__device__ __forceinline__ void store_padded(double* __restrict__ r12, int64_t c, const double* rot) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r12[GSTRIDE * c + 4 * i + j] = rot[3 * i + j];
+        r12[GSTRIDE * c + 4 * i + 3] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(NODE_THREADS) gauge_project_kernel(const double* __restrict__ V, double* __restrict__ r_c, int64_t n_c,
+                                                                   double* __restrict__ r12 = nullptr) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_c) return;
     double v0[9], v0i[9], v[9], x[9], rot[9];
@@ -48,11 +59,12 @@ __global__ void __launch_bounds__(NODE_THREADS) gauge_project_kernel(const doubl
     node_factors(x, rot, nullptr, nullptr);
 #pragma unroll
     for (int i = 0; i < 9; ++i) r_c[9 * c + i] = rot[i];
+    if (r12) store_padded(r12, c, rot);
 }
 
 // bipgo.py:306-315
 __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const double* __restrict__ M, double* __restrict__ r_c, double* __restrict__ lamC,
-                                     double* __restrict__ lamCinv, int64_t n_c) {
+                                     double* __restrict__ lamCinv, int64_t n_c, double* __restrict__ r12 = nullptr) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_c) return;
     double m[9], rot[9], sp[9], si[9];
@@ -65,6 +77,7 @@ __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const doubl
         lamC[9 * c + i] = sp[i];
         if (lamCinv) lamCinv[9 * c + i] = si[i];
     }
+    if (r12) store_padded(r12, c, rot);
 }
 
 // bipgo.py:323-332 (+ Wt = Lambda_T Y_t, the time half of the next L-apply).  Yt12 / Wt12 use the
@@ -202,9 +215,10 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     };
     auto prof_end = [&](int slot) { if (slot >= 0) cudaEventRecord(pst.prof[2 * slot + 1], st); };
 
-    auto time_pass = [&](int mode, const double* X, double* out, const double* skip = nullptr) -> int {
-        S->time_passes++; S->kernel_launches += 2;
-        int rc = launch_pad_blocks(X, w.Xpad, n_c, st, skip);   // gather source layout: 3 rows x 4 doubles
+    // prepadded: the producer of X (LOBPCG step, gauge / primal kernels) already wrote w.Xpad
+    auto time_pass = [&](int mode, const double* X, double* out, const double* skip = nullptr, bool prepadded = false) -> int {
+        S->time_passes++; S->kernel_launches += prepadded ? 1 : 2;
+        int rc = prepadded ? 0 : launch_pad_blocks(X, w.Xpad, n_c, st, skip);   // gather source layout: 3 rows x 4 doubles
         if (rc) return rc;
         const int slot = prof_begin(0);
         rc = launch_pass_time(mode, g->t_rowptr, g->t_cam, g->t_B, w.Xpad, w.lamT, out, n_t, st, skip);
@@ -249,16 +263,15 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     lp.X = w.X; lp.AX = w.AX; lp.W = w.W; lp.AW = w.AW; lp.P = w.P; lp.AP = w.AP;
     lp.Y = w.Y; lp.lamC = w.lamC; lp.lamCinv = w.lamCinv; lp.small = w.small; lp.partial = w.partial;
     lp.tol = opt->tol;
+    lp.Wpad = w.Xpad;
     const int max_inner = opt->max_inner > 0 ? opt->max_inner : 200;
     static const bool lob_timing = getenv("VICAN_B200_LOBPCG_TIMING") != nullptr;   // diagnostics: stage times of every step
 
     for (int outer = 0; outer < opt->maxiter; ++outer) {
         if (outer == 0) VB_RC(time_pass(0, w.X, w.Wt));
         VB_RC(cam_pass(w.Wt, w.Y));
-        VB_CHECK(cudaMemsetAsync(w.W, 0, cbytes, st));
-        VB_CHECK(cudaMemsetAsync(w.AW, 0, cbytes, st));
-        VB_CHECK(cudaMemsetAsync(w.P, 0, cbytes, st));
-        VB_CHECK(cudaMemsetAsync(w.AP, 0, cbytes, st));
+        // W, AW, P, AP are carved back to back: one memset
+        VB_CHECK(cudaMemsetAsync(w.W, 0, (size_t)((char*)w.AP - (char*)w.W) + cbytes, st));
         lp.first = 1;
         VB_RC(launch_lobpcg_step(lp, st));
         S->lobpcg_steps++; S->kernel_launches++;
@@ -280,7 +293,7 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         for (;;) {
             bool speculated = false;
             if (enqueued < max_inner) {
-                VB_RC(time_pass(0, w.W, w.Wt, conv_flag));
+                VB_RC(time_pass(0, w.W, w.Wt, conv_flag, true));   // the step kernel wrote W into Xpad as well
                 VB_RC(cam_pass(w.Wt, w.Y, conv_flag));
                 lp.first = 0;
                 VB_RC(launch_lobpcg_step(lp, st));
@@ -325,13 +338,13 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         for (int j = 0; j < 3; ++j) { S->theta[j] = hs[SM_THETA + j]; S->resid[j] = hs[SM_RESN + j]; }
         S->anorm = hs[SM_ANORM];
 
-        gauge_project_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, r_c, n_c);
+        gauge_project_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, r_c, n_c, w.Xpad);
         VB_KERNEL_CHECK();
-        VB_RC(time_pass(0, r_c, w.Wt));
+        VB_RC(time_pass(0, r_c, w.Wt, nullptr, true));
         VB_RC(cam_pass(w.Wt, w.Y));
-        primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, w.lamC, w.lamCinv, n_c);
+        primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, w.lamC, w.lamCinv, n_c, w.Xpad);
         VB_KERNEL_CHECK();
-        VB_RC(time_pass(1, r_c, w.Wt));
+        VB_RC(time_pass(1, r_c, w.Wt, nullptr, true));
         if (n_t > 0) dual_update_kernel<<<node_grid(n_t), NODE_THREADS, 0, st>>>(w.Wt, r_t, w.lamT, w.Wt, n_t);
         VB_KERNEL_CHECK();
         S->kernel_launches += 3;
