@@ -259,9 +259,10 @@ def main():
 
     # ---- per-kernel roofline: the two edge passes, timed alone with CUDA events (inputs 3.9 GB >> L2)
     import ctypes as C
-    X = torch.randn((n_c, 12), dtype=torch.float64, device=dev)       # padded gather layout (3 rows x 4)
+    gs = int(lib.vb_gather_stride())                                   # padded gather layout (3 rows x 4, one 128-byte line)
+    X = torch.randn((n_c, gs), dtype=torch.float64, device=dev)
     lamT = torch.randn((g.n_t, 9), dtype=torch.float64, device=dev)
-    Wt = torch.zeros((g.n_t, 12), dtype=torch.float64, device=dev)
+    Wt = torch.zeros((g.n_t, gs), dtype=torch.float64, device=dev)
     Y = torch.zeros((n_c, 9), dtype=torch.float64, device=dev)
     ptr, stream = solver._ptr, solver._stream
     kern = {}

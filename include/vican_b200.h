@@ -159,10 +159,12 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
 
 /* ---- rotation stage (bipgo.py:243-348) --------------------------------------------------- */
 /* One edge pass each (exposed for tests and for the roofline measurement).  Gathered node
- * blocks use the PADDED layout [n][12] (3 rows x 4 doubles, row = 32 bytes) so that one row is
- * one 256-bit load; vb_pad_blocks converts a compact [n][9] array.
+ * blocks use the PADDED layout [n][S], S = vb_gather_stride() doubles (3 rows x 4 doubles, row = 32
+ * bytes, then padding up to one 128-byte line) so that one row is one 256-bit load and the three
+ * rows of a block share an L1 line; vb_pad_blocks converts a compact [n][9] array.
  *   vb_pass_time: out12_t = [Lambda_T[t]] * sum_{e in t} B_e^T X12[c_e]  (mode 0 with lamT [n_t][9], mode 1 raw sum)
  *   vb_pass_cam : Y_c    += sum_{e in c} B_e W12[t_e]      (Y compact [n_c][9], zeroed by the caller) */
+int vb_gather_stride(void);
 int vb_pad_blocks(const double* src9, double* dst12, int64_t n, void* stream);
 int vb_pass_time(const vb_graph* g, int mode, const double* X12, const double* lamT, double* out12, void* stream);
 int vb_pass_cam(const vb_graph* g, const double* W12, double* Y, void* stream);

@@ -154,12 +154,13 @@ def test_edge_passes_match_numpy(cuda, shape, tile_len):
     W0 = lamT @ Z0
     Y0 = dm.pass_cam(pc, pt, B, W0, a["n_c"])
     Xd = torch.as_tensor(X.reshape(-1, 9)).cuda()
-    X12 = torch.empty((a["n_c"], 12), dtype=torch.float64, device="cuda")
+    gs = cuda.vb_gather_stride()                       # padded gather layout: 3 rows x 4 doubles (+ padding to a 128-byte line)
+    X12 = torch.empty((a["n_c"], gs), dtype=torch.float64, device="cuda")
     assert cuda.vb_pad_blocks(_ptr(Xd), _ptr(X12), a["n_c"], _stream()) == 0
-    assert np.array_equal(X12.cpu().numpy().reshape(-1, 3, 4)[:, :, :3], X)
+    assert np.array_equal(X12.cpu().numpy()[:, :12].reshape(-1, 3, 4)[:, :, :3], X)
     Ld = torch.as_tensor(lamT.reshape(-1, 9)).cuda()
-    out = torch.zeros((a["n_t"], 12), dtype=torch.float64, device="cuda")
-    unpad = lambda t: t.cpu().numpy().reshape(-1, 3, 4)[:, :, :3]  # noqa: E731
+    out = torch.zeros((a["n_t"], gs), dtype=torch.float64, device="cuda")
+    unpad = lambda t: t.cpu().numpy()[:, :12].reshape(-1, 3, 4)[:, :, :3]  # noqa: E731
     assert cuda.vb_pass_time(C.byref(dg.cgraph), 1, _ptr(X12), None, _ptr(out), _stream()) == 0
     assert np.abs(unpad(out) - Z0).max() < 1e-12 * np.abs(Z0).max()
     assert cuda.vb_pass_time(C.byref(dg.cgraph), 0, _ptr(X12), _ptr(Ld), _ptr(out), _stream()) == 0

@@ -38,8 +38,9 @@ def big(cuda):
 def _apply(cuda, g, X9, lamT):
     """Y = P Lambda_T P^T X through the two edge passes."""
     from vican_b200.solver import _ptr, _stream
-    X12 = torch.empty((g.n_c, 12), dtype=torch.float64, device="cuda")
-    W12 = torch.zeros((g.n_t, 12), dtype=torch.float64, device="cuda")
+    gs = cuda.vb_gather_stride()
+    X12 = torch.empty((g.n_c, gs), dtype=torch.float64, device="cuda")
+    W12 = torch.zeros((g.n_t, gs), dtype=torch.float64, device="cuda")
     Y = torch.zeros((g.n_c, 9), dtype=torch.float64, device="cuda")
     assert cuda.vb_pad_blocks(_ptr(X9), _ptr(X12), g.n_c, _stream()) == 0
     assert cuda.vb_pass_time(C.byref(g.cgraph), 0, _ptr(X12), _ptr(lamT), _ptr(W12), _stream()) == 0

@@ -16,6 +16,9 @@
 namespace vb {
 
 constexpr unsigned FULL = 0xffffffffu;
+// doubles per gathered node block (padded gather layout): 3 rows x (3 + 1 pad) = 96 bytes, padded to one
+// 128-byte line so that the three 32-byte row loads of an edge never straddle two L1 lines
+constexpr int GSTRIDE = 16;
 constexpr int NUM_SMS_B200 = 148;
 
 inline int sm_count() {

@@ -38,7 +38,7 @@ struct LobpcgParams {
     const double *lamC, *lamCinv;
     double* small;
     double* partial;   // [3][gridDim.x][LOB_NRED]
-    double* Wpad;      // new W also in the padded gather layout [n_c][12] (input of the next time pass)
+    double* Wpad;      // new W also in the padded gather layout [n_c][GSTRIDE] (input of the next time pass)
     double tol;
     int first;
 };
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
             }
             row_times(w, T, wn);
             st3(p.W + o, wn);
-            if (p.Wpad) { double* q = p.Wpad + 4 * (size_t)r; q[0] = wn[0]; q[1] = wn[1]; q[2] = wn[2]; q[3] = 0.0; }
+            if (p.Wpad) { double* q = p.Wpad + GSTRIDE * (size_t)(r / 3) + 4 * irow; q[0] = wn[0]; q[1] = wn[1]; q[2] = wn[2]; q[3] = 0.0; }
         }
     lob_stamp(p, 9);
 }

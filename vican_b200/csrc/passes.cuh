@@ -38,7 +38,6 @@
 
 namespace vb {
 
-constexpr int GSTRIDE = 12;   // doubles per gathered node block: 3 rows x (3 + 1 pad)
 
 constexpr int PASS_THREADS = 128;          // 4 independent warp pipelines per CTA
 constexpr int PASS_CTAS_PER_SM = 4;        // 4 x ~42 KB shared memory, <= 127 registers
@@ -347,20 +346,20 @@ edge_pass_fused_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ 
     peer_reduce(pd, epoch, Y, n_y);
 }
 
-// compact [n][9] -> padded [n][12] node blocks (the gather source layout)
+// compact [n][9] -> padded [n][GSTRIDE] node blocks (the gather source layout)
 __global__ void pad_blocks_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n,
                                   const double* __restrict__ skip_flag) {
     if (skip_flag != nullptr && *skip_flag != 0.0) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 12 * n) return;
-    const int64_t node = i / 12;
-    const int c = (int)(i - 12 * node), row = c >> 2, col = c & 3;
-    dst[i] = (col < 3) ? src[9 * node + 3 * row + col] : 0.0;
+    if (i >= GSTRIDE * n) return;
+    const int64_t node = i / GSTRIDE;
+    const int c = (int)(i - GSTRIDE * node), row = c >> 2, col = c & 3;
+    dst[i] = (row < 3 && col < 3) ? src[9 * node + 3 * row + col] : 0.0;
 }
 
 inline int launch_pad_blocks(const double* src, double* dst, int64_t n, cudaStream_t st, const double* skip_flag = nullptr) {
     if (n <= 0) return 0;
-    pad_blocks_kernel<<<(int)((12 * n + 255) / 256), 256, 0, st>>>(src, dst, n, skip_flag);
+    pad_blocks_kernel<<<(int)((GSTRIDE * n + 255) / 256), 256, 0, st>>>(src, dst, n, skip_flag);
     VB_KERNEL_CHECK();
     return 0;
 }
@@ -408,7 +407,7 @@ inline int launch_pass_cam_fused(const int* tile_cam, const int* tile_start, con
 
 // NOTE: idx must be readable up to index ((E+3)&~3)-1 and B up to edge ((E+1)&~1)-1 (the bulk
 // copies are 16-byte granular); the ingestion allocates that padding.
-// X12: padded gather source [n_c][12]; out12: padded [n_t][12].
+// X12: padded gather source [n_c][GSTRIDE]; out12: padded [n_t][GSTRIDE].
 inline int launch_pass_time(int mode, const int* rowptr, const int* cam, const double* B, const double* X12,
                             const double* lamT, double* out12, int64_t n_t, cudaStream_t st,
                             const double* skip_flag = nullptr) {

@@ -68,6 +68,8 @@ extern "C" {
 
 const char* vb_version(void) { return "vican_b200 0.1.0 (sm_100a)"; }
 
+int vb_gather_stride(void) { return GSTRIDE; }
+
 const char* vb_status_string(int code) {
     if (code < 0) return cudaGetErrorString((cudaError_t)(-code));
     switch (code) {
