@@ -46,7 +46,7 @@ typedef struct vb_graph {
     const int32_t* c_segptr;   /* [n_windows*n_c+1] runs of the camera-pass order: run (w, c) = [c_segptr[w*n_c+c], +1) */
     const int32_t* c_order;    /* [E]   camera-pass position -> time-sorted edge */
     const int32_t* c_time;     /* [E]   time node of each camera-pass edge ((window, camera, time) order) */
-    const double*  c_B;        /* [E][9] */
+    const double*  c_B;        /* [E][9] the same blocks TRANSPOSED (B_e^T), camera-pass order */
     const double*  c_w;        /* [E] */
     const int32_t* tile_cam;   /* [n_tiles] */
     const int32_t* tile_start; /* [n_tiles] */
@@ -163,7 +163,8 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
  * bytes, then padding up to one 128-byte line) so that one row is one 256-bit load and the three
  * rows of a block share an L1 line; vb_pad_blocks converts a compact [n][9] array.
  *   vb_pass_time: out12_t = [Lambda_T[t]] * sum_{e in t} B_e^T X12[c_e]  (mode 0 with lamT [n_t][9], mode 1 raw sum)
- *   vb_pass_cam : Y_c    += sum_{e in c} B_e W12[t_e]      (Y compact [n_c][9], zeroed by the caller) */
+ *   vb_pass_cam : Y_c    += sum_{e in c} B_e W12[t_e]      (Y compact [n_c][9], zeroed by the caller;
+ *                 g->c_B holds the blocks transposed, as vb_ingest_build writes them) */
 int vb_gather_stride(void);
 int vb_pad_blocks(const double* src9, double* dst12, int64_t n, void* stream);
 int vb_pass_time(const vb_graph* g, int mode, const double* X12, const double* lamT, double* out12, void* stream);

@@ -112,7 +112,8 @@ def test_ingestion_matches_oracle_aggregation(cuda, shape, shuffle):
     cord = dg.c_order.cpu().numpy()                       # camera-pass order: (time window, camera, time)
     assert sorted(cord.tolist()) == list(range(dg.n_edges))
     assert np.array_equal(dg.c_time.cpu().numpy(), pt[order][cord])
-    assert np.array_equal(dg.c_B.cpu().numpy(), dg.t_B.cpu().numpy()[cord])
+    # the camera-pass copy stores the blocks transposed (conflict-free column reads in the pass)
+    assert np.array_equal(dg.c_B.cpu().numpy().reshape(-1, 3, 3), np.transpose(dg.t_B.cpu().numpy()[cord].reshape(-1, 3, 3), (0, 2, 1)))
     assert np.array_equal(dg.c_w.cpu().numpy(), dg.t_w.cpu().numpy()[cord])
     deg_t = np.zeros(a["n_t"]); np.add.at(deg_t, pt, av)
     deg_c = np.zeros(a["n_c"]); np.add.at(deg_c, pc, av)

@@ -114,13 +114,16 @@ __global__ void seg_ptr_kernel(const int* __restrict__ node_sorted, const int* _
 __global__ void gather_cam_sorted_kernel(const int* __restrict__ c_perm, const int* __restrict__ t_time, const double* __restrict__ t_B,
                                          const double* __restrict__ t_w, int* __restrict__ c_time, double* __restrict__ c_B,
                                          double* __restrict__ c_w, int64_t n) {
-    // 9 threads per edge: coalesced 72-byte record copies
+    // 9 threads per edge: coalesced 72-byte record copies.  The camera-pass copy holds the blocks
+    // TRANSPOSED: the camera pass needs COLUMN k of B_e per lane, and with B^T in the stage that is a
+    // contiguous row (conflict-free LDS.64, like the time pass) instead of a stride-3 column whose
+    // shared-memory reads were 2-way bank conflicted (30 M of 156 M L1 wavefronts per pass, ncu)
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i = gid / 9;
     const int k = (int)(gid - 9 * i);
     if (i >= n) return;
     const int64_t src = c_perm[i];
-    c_B[9 * i + k] = t_B[9 * src + k];
+    c_B[9 * i + k] = t_B[9 * src + 3 * (k % 3) + k / 3];
     if (k == 0) { c_time[i] = t_time[src]; c_w[i] = t_w[src]; }
 }
 

@@ -96,10 +96,12 @@ __device__ __forceinline__ void edge_rounds(const double* __restrict__ sB, const
         x[u][0] = x[u][1] = x[u][2] = 0.0;
         if (on) {
             const int node = sI[offI + off];
-            const double* pb = sB + 9 * (offB + off) + (TR ? 3 * k : k);
+            // row k of the staged block: row k of B for the time pass, row k of B^T (= column k of B) for the
+            // camera pass, whose copy of the blocks is stored transposed
+            const double* pb = sB + 9 * (offB + off) + 3 * k;
             b[u][0] = pb[0];
-            b[u][1] = pb[TR ? 1 : 3];
-            b[u][2] = pb[TR ? 2 : 6];
+            b[u][1] = pb[1];
+            b[u][2] = pb[2];
             ld_row256(G + GSTRIDE * (size_t)node + 4 * k, x[u][0], x[u][1], x[u][2]);
         }
     }
@@ -166,10 +168,12 @@ __device__ __forceinline__ void item_load(const unsigned char* bufp, const doubl
         x[u][0] = x[u][1] = x[u][2] = 0.0;
         if ((e < EDGES_PER_ROUND) && (off < n_e)) {
             const int node = sI[offI + off];
-            const double* pb = sB + 9 * (offB + off) + (TR ? 3 * k : k);
+            // row k of the staged block: row k of B for the time pass, row k of B^T (= column k of B) for the
+            // camera pass, whose copy of the blocks is stored transposed
+            const double* pb = sB + 9 * (offB + off) + 3 * k;
             b[u][0] = pb[0];
-            b[u][1] = pb[TR ? 1 : 3];
-            b[u][2] = pb[TR ? 2 : 6];
+            b[u][1] = pb[1];
+            b[u][2] = pb[2];
             ld_row256(G + GSTRIDE * (size_t)node + 4 * k, x[u][0], x[u][1], x[u][2]);
         }
     }
