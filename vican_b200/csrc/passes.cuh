@@ -19,10 +19,11 @@
 //    blocks and 4-byte indices) into the warp's double-buffered shared-memory stage with two
 //    cp.async.bulk copies (TMA, mbarrier completion, L2 evict-first) while the warp consumes
 //    the current item.  No CTA-wide synchronisation exists.
-//  * lane mapping: 30 lanes = 10 edges x 3 rows.  Lane (e, k) reads row k (column k in the
-//    camera pass) of edge e's block from shared memory (3 LDS.64, conflict-free) and row k of
-//    the gathered node block with ONE 256-bit load (node blocks are stored padded, 3 rows of
-//    4 doubles = 96 bytes, so a row is 32-byte aligned), then does the 9 FMAs of
+//  * lane mapping: 30 lanes = 10 edges x 3 rows.  Lane (e, k) reads row k of edge e's staged
+//    block from shared memory (3 LDS.64, conflict-free; the camera-pass copy of the blocks is
+//    stored transposed, so its "row k" is column k of B_e) and row k of the gathered node block
+//    with ONE 256-bit load (node blocks are stored padded: 3 rows of 4 doubles in one 128-byte
+//    line, so a row is 32-byte aligned and an edge touches one L1 line), then does the 9 FMAs of
 //    B[k][:]^T x G[k][:] into a private 3x3 accumulator.  No shuffles in the inner loop: the
 //    previous mapping (9 lanes per edge, row broadcast by shuffles) was bound by the LSU /
 //    shuffle return path at 52-60 % of the HBM roofline.
@@ -77,40 +78,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // one 32-byte row of a padded node block; gathered blocks are re-read by many edges -> keep in L2
 // (the default L2 policy instead of evict-last measured 3-5 % slower inside the solve)
 __device__ __forceinline__ void ld_row256(const double* p, double& a, double& b, double& c) {
-    double d;
-    asm volatile("ld.global.nc.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-
-// NR rounds of 10 edges.  acc[3a+j] += b_a * g_j with (b_0..2) = row k of B (TR) / column k of B (!TR)
-// and (g_0..2) = row k of the gathered block:  TR -> (B^T G)[a][j],  !TR -> (B G)[a][j].
-template <bool TR, int NR>
-__device__ __forceinline__ void edge_rounds(const double* __restrict__ sB, const int* __restrict__ sI,
-                                            const double* __restrict__ G, int offB, int offI, int g0, int n_e,
-                                            int e, int k, double (&acc)[9]) {
-    double b[NR][3], x[NR][3];
-#pragma unroll
-    for (int u = 0; u < NR; ++u) {
-        const int off = g0 + EDGES_PER_ROUND * u + e;
-        const bool on = (e < EDGES_PER_ROUND) && (off < n_e);
-        b[u][0] = b[u][1] = b[u][2] = 0.0;
-        x[u][0] = x[u][1] = x[u][2] = 0.0;
-        if (on) {
-            const int node = sI[offI + off];
-            // row k of the staged block: row k of B for the time pass, row k of B^T (= column k of B) for the
-            // camera pass, whose copy of the blocks is stored transposed
-            const double* pb = sB + 9 * (offB + off) + 3 * k;
-            b[u][0] = pb[0];
-            b[u][1] = pb[1];
-            b[u][2] = pb[2];
-            ld_row256(G + GSTRIDE * (size_t)node + 4 * k, x[u][0], x[u][1], x[u][2]);
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < NR; ++u)
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) acc[3 * a + j] = fma(b[u][a], x[u][j], acc[3 * a + j]);
+    double pad;   // 4th double of the row: padding
+    asm volatile("ld.global.nc.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(pad) : "l"(p));
+    (void)pad;
 }
 
 // Sum 9 values over the 32 lanes with a reduce-scatter butterfly: at every step a lane keeps
@@ -155,7 +125,6 @@ struct Item {
 };
 
 // item loads: block rows (LDS) + far-endpoint indices (LDS) + 256-bit row gathers, all issued back to back
-template <bool TR>
 __device__ __forceinline__ void item_load(const unsigned char* bufp, const double* __restrict__ G, const Item& it, int e,
                                           int k, double (&b)[5][3], double (&x)[5][3]) {
     const double* sB = reinterpret_cast<const double*>(bufp);
@@ -206,7 +175,6 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
                                                const double* __restrict__ G, const double* __restrict__ lamT,
                                                double* __restrict__ out, int n_seg) {
     extern __shared__ __align__(128) unsigned char pass_smem[];
-    constexpr bool TR = (MODE != 2);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * PASS_WARPS + wib;
     const int nwarps = gridDim.x * PASS_WARPS;
@@ -270,7 +238,7 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     double lamC[3] = {0.0, 0.0, 0.0}, lamN[3] = {0.0, 0.0, 0.0};
     auto load = [&](const Item& it, int buf, double (&lam)[3]) {
         if (!it.valid) return;
-        item_load<TR>(wbuf + buf * BUF_BYTES, G, it, e, k, bq, xq);
+        item_load(wbuf + buf * BUF_BYTES, G, it, e, k, bq, xq);
         if (MODE == 0 && it.last && lane < 9) {   // Lambda_T row for this segment's epilogue
             if (lamT != nullptr) {
                 const double* L = lamT + 9 * (size_t)it.seg + 3 * (lane / 3);
