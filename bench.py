@@ -318,6 +318,7 @@ def main():
                                            for f in ("cam", "time", "marker", "R", "t", "k_r", "k_t")})
         h2d = sum(getattr(host, f).numel() * getattr(host, f).element_size()
                   for f in ("cam", "time", "marker", "R", "t", "k_r", "k_t"))
+        barrier()          # pinning the host buffers takes seconds and not the same time on every rank
         one_solve(host, to_host=True)
         k_e2e = max(1, min(args.steps, 3))
         barrier(); torch.cuda.synchronize()
