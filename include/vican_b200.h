@@ -66,7 +66,7 @@ typedef struct vb_so3_options {
     vb_allreduce_fn allreduce;
     void*   allreduce_ctx;
     int32_t profile_events; /* != 0: bracket every edge-pass launch with CUDA events (stats->*_pass_ms) */
-    int32_t reserved;
+    int32_t no_shortcut;    /* != 0: always run the primal multiply as two edge passes (see stats->shortcut_outer) */
     void*   peer_ctx;       /* vb_peer_create context: the camera pass runs FUSED with its cross-rank sum over
                              * NVLink peer memory (allreduce / allreduce_ctx are then used for the few other
                              * reductions only and may point at vb_peer_allreduce); NULL: separate collective */
@@ -89,6 +89,11 @@ typedef struct vb_so3_stats {
     double  cam_pass_ms;    /* sum over executed camera passes */
     int32_t time_pass_timed;
     int32_t cam_pass_timed;
+    /* outer iterations whose primal multiply was obtained WITHOUT edge passes: when the eigen-iteration accepts
+     * its start block R (the previous r_c) at the first step, project_SO3(V_c V_0^-1) = R_c R_0^T exactly and
+     * P Lambda_T P^T r_c = Y R_0^T with Y already computed for the eigen-residual (bipgo.py:295-300) */
+    int32_t shortcut_outer;
+    int32_t reserved2;
 } vb_so3_stats;
 
 const char* vb_version(void);

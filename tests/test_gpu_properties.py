@@ -176,3 +176,19 @@ def test_cfg5_convergence_stress_matches_oracle(cuda, filtered, outliers, maxite
     inner = list(rot.stats.inner_per_outer[:min(maxiter, 64)])
     assert inner[-1] <= 2 and sum(inner[10:]) <= 2 * len(inner[10:]), inner
     assert rot.stats.time_passes <= 2 * maxiter + sum(inner) + 40
+
+
+def test_primal_shortcut_equals_the_two_pass_multiply(cuda, big):
+    """When the eigen-iteration accepts its start block at the first step, project_SO3(V_c V_0^-1) = R_c R_0^T
+    and the primal multiply is Y R_0^T (no edge passes).  Same result as the explicit two-pass multiply to
+    rounding, with 2 passes less per converged outer iteration."""
+    from vican_b200 import solver
+    det, g = big
+    a = solver.solve_rotations(g, 12, shortcut=True)
+    b = solver.solve_rotations(g, 12, shortcut=False)
+    assert b.stats.shortcut_outer == 0 and a.stats.shortcut_outer >= 6
+    assert a.stats.time_passes == b.stats.time_passes - a.stats.shortcut_outer
+    assert a.stats.cam_passes == b.stats.cam_passes - a.stats.shortcut_outer
+    assert list(a.stats.inner_per_outer[:12]) == list(b.stats.inner_per_outer[:12])
+    assert geodesic_rad(a.r_c.cpu().numpy(), b.r_c.cpu().numpy()).max() < 1e-12
+    assert geodesic_rad(a.r_t.cpu().numpy(), b.r_t.cpu().numpy()).max() < 1e-12

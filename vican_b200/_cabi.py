@@ -40,7 +40,7 @@ class VbGraph(C.Structure):
 
 class VbSo3Options(C.Structure):
     _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP),
-                ("profile_events", I32), ("reserved", I32), ("peer_ctx", VP)]
+                ("profile_events", I32), ("no_shortcut", I32), ("peer_ctx", VP)]
 
 
 class VbSo3Stats(C.Structure):
@@ -49,6 +49,7 @@ class VbSo3Stats(C.Structure):
         ("kernel_launches", I32), ("stalled_outer", I32),
         ("theta", F64 * 3), ("resid", F64 * 3), ("anorm", F64), ("inner_per_outer", I32 * 64),
         ("time_pass_ms", F64), ("cam_pass_ms", F64), ("time_pass_timed", I32), ("cam_pass_timed", I32),
+        ("shortcut_outer", I32), ("reserved2", I32),
     ]
 
 

@@ -62,6 +62,27 @@ __global__ void __launch_bounds__(NODE_THREADS) gauge_project_kernel(const doubl
     if (r12) store_padded(r12, c, rot);
 }
 
+// Y_c <- Y_c R0^T for every camera block (R0: 9 doubles on the device).  Used when the eigen-iteration
+// accepts its start block unchanged: see the shortcut in so3sync_run.
+__global__ void __launch_bounds__(NODE_THREADS) rotate_right_transposed_kernel(double* __restrict__ Y, const double* __restrict__ R0, int64_t n_c) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_c) return;
+    double m[9], r0[9], o[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { m[i] = Y[9 * c + i]; r0[i] = R0[i]; }
+    mmt3(m, r0, o);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Y[9 * c + i] = o[i];
+}
+
+// Y = 0 unless the convergence flag is set (speculative camera passes must leave Y alone once the
+// eigen-iteration has converged: the shortcut below reuses it)
+__global__ void cond_zero_kernel(double* __restrict__ Y, int64_t n, const double* __restrict__ skip_flag) {
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) Y[i] = 0.0;
+}
+
 // bipgo.py:306-315
 __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const double* __restrict__ M, double* __restrict__ r_c, double* __restrict__ lamC,
                                      double* __restrict__ lamCinv, int64_t n_c, double* __restrict__ r12 = nullptr) {
@@ -236,7 +257,8 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
             last_cam_slot = slot;
             return rc;
         }
-        VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
+        if (skip == nullptr) VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
+        else { cond_zero_kernel<<<node_grid(9 * n_c), NODE_THREADS, 0, st>>>(Y, 9 * n_c, skip); S->kernel_launches++; }
         S->cam_passes++; S->kernel_launches++;
         const int slot = prof_begin(1);
         int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, Wt, Y, g->n_tiles, st, skip);
@@ -338,10 +360,24 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         for (int j = 0; j < 3; ++j) { S->theta[j] = hs[SM_THETA + j]; S->resid[j] = hs[SM_RESN + j]; }
         S->anorm = hs[SM_ANORM];
 
-        gauge_project_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, r_c, n_c, w.Xpad);
-        VB_KERNEL_CHECK();
-        VB_RC(time_pass(0, r_c, w.Wt, nullptr, true));
-        VB_RC(cam_pass(w.Wt, w.Y));
+        // Primal multiply M = P Lambda_T P^T r_c with r_c = project_SO3(V_c V_0^-1) (bipgo.py:295-300).
+        // Shortcut: when the eigen-iteration accepted its start block at the FIRST step (inner == 1), the new
+        // eigenvectors are V = R C with R = the previous r_c (blocks in SO(3)) and C a 3x3 matrix, so
+        // V_c V_0^-1 = R_c C C^-1 R_0^-1 = R_c R_0^T is already a rotation, r_c = R R_0^T, and
+        // M = (P Lambda_T P^T R) R_0^T = Y R_0^T with Y the camera-pass result this very iteration started
+        // from: no gauge kernel, no time pass, no camera pass (2 instead of 4 edge passes per converged
+        // outer iteration).  Y and the old r_c are still intact here (speculative passes leave Y alone).
+        const bool shortcut = opt->no_shortcut == 0 && outer >= 1 && inner == 1 && hs[SM_CONV] != 0.0;
+        if (shortcut) {
+            rotate_right_transposed_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, n_c);
+            VB_KERNEL_CHECK();
+            S->shortcut_outer++;
+        } else {
+            gauge_project_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, r_c, n_c, w.Xpad);
+            VB_KERNEL_CHECK();
+            VB_RC(time_pass(0, r_c, w.Wt, nullptr, true));
+            VB_RC(cam_pass(w.Wt, w.Y));
+        }
         primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, w.lamC, w.lamCinv, n_c, w.Xpad);
         VB_KERNEL_CHECK();
         VB_RC(time_pass(1, r_c, w.Wt, nullptr, true));

@@ -213,7 +213,9 @@ class RotationResult:
 
 
 def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner: int = 200,
-                    comm: Optional[Comm] = None, profile_events: bool = False) -> RotationResult:
+                    comm: Optional[Comm] = None, profile_events: bool = False, shortcut: bool = True) -> RotationResult:
+    """``shortcut=False`` forces the primal multiply through its two edge passes in every outer
+    iteration (see ``vb_so3_stats.shortcut_outer``); the results agree to rounding."""
     lib = _cabi.lib()
     dev = g.device
     with torch.cuda.device(dev):
@@ -223,7 +225,8 @@ def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner:
         r_t = torch.empty((g.n_t, 9), dtype=F64, device=dev)
         fn, fctx = comm.reducer(lib, 9 * g.n_c) if comm is not None else (None, None)
         fused = comm.peer if (comm is not None and comm.peer is not None and 9 * g.n_c <= comm.peer_capacity) else None
-        opt = VbSo3Options(int(maxiter), int(max_inner), float(tol), fn, fctx, 1 if profile_events else 0, 0, fused)
+        opt = VbSo3Options(int(maxiter), int(max_inner), float(tol), fn, fctx, 1 if profile_events else 0,
+                           0 if shortcut else 1, fused)
         stats = VbSo3Stats()
         rc = lib.vb_so3sync_run(C.byref(g.cgraph), C.byref(opt), _ptr(r_c), _ptr(r_t), _ptr(ws), wsb,
                                 C.byref(stats), _stream())
