@@ -159,7 +159,7 @@ __global__ void svd_factors_batch_kernel(const double* __restrict__ M, double* r
 inline int64_t align256(int64_t b) { return (b + 255) & ~(int64_t)255; }
 
 struct So3Work {
-    double *X, *AX, *W, *AW, *P, *AP, *Y, *lamC, *lamCinv, *degc, *Xpad, *lamT, *Wt, *small, *partial;
+    double *X, *AX, *W, *AW, *P, *AP, *Y, *Ykeep, *lamC, *lamCinv, *degc, *Xpad, *lamT, *Wt, *small, *partial;
     int64_t bytes;
 };
 
@@ -173,7 +173,7 @@ inline So3Work carve_so3(void* base, int64_t n_c, int64_t n_t) {
         return r;
     };
     w.X = take(9 * n_c); w.AX = take(9 * n_c); w.W = take(9 * n_c); w.AW = take(9 * n_c);
-    w.P = take(9 * n_c); w.AP = take(9 * n_c); w.Y = take(9 * n_c);
+    w.P = take(9 * n_c); w.AP = take(9 * n_c); w.Y = take(9 * n_c); w.Ykeep = take(9 * n_c);
     w.lamC = take(9 * n_c); w.lamCinv = take(9 * n_c); w.degc = take(n_c);
     w.Xpad = take(GSTRIDE * n_c);
     w.lamT = take(9 * n_t); w.Wt = take(GSTRIDE * n_t);
@@ -292,6 +292,11 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     for (int outer = 0; outer < opt->maxiter; ++outer) {
         if (outer == 0) VB_RC(time_pass(0, w.X, w.Wt));
         VB_RC(cam_pass(w.Wt, w.Y));
+        // A host-issued collective (NCCL hook without the fused peer path) also runs for the speculative camera
+        // pass that follows a converged step and would sum the already summed Y once more: keep a copy for the
+        // shortcut below.  (The fused kernel and the single-GPU path leave Y alone when the flag is set.)
+        const bool keep_Y = opt->allreduce != nullptr && opt->peer_ctx == nullptr;
+        if (keep_Y) VB_CHECK(cudaMemcpyAsync(w.Ykeep, w.Y, cbytes, cudaMemcpyDeviceToDevice, st));
         // W, AW, P, AP are carved back to back: one memset
         VB_CHECK(cudaMemsetAsync(w.W, 0, (size_t)((char*)w.AP - (char*)w.W) + cbytes, st));
         lp.first = 1;
@@ -369,6 +374,7 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         // outer iteration).  Y and the old r_c are still intact here (speculative passes leave Y alone).
         const bool shortcut = opt->no_shortcut == 0 && outer >= 1 && inner == 1 && hs[SM_CONV] != 0.0;
         if (shortcut) {
+            if (keep_Y) VB_CHECK(cudaMemcpyAsync(w.Y, w.Ykeep, cbytes, cudaMemcpyDeviceToDevice, st));
             rotate_right_transposed_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, n_c);
             VB_KERNEL_CHECK();
             S->shortcut_outer++;
