@@ -67,6 +67,9 @@ typedef struct vb_so3_options {
     void*   allreduce_ctx;
     int32_t profile_events; /* != 0: bracket every edge-pass launch with CUDA events (stats->*_pass_ms) */
     int32_t no_shortcut;    /* != 0: always run the primal multiply as two edge passes (see stats->shortcut_outer) */
+    int32_t identity_start; /* != 0: first eigen-solve starts from identity blocks instead of the one-hop spanning
+                             * estimate project_SO3((P Lambda_T P^T E_0)_c) (2 extra edge passes, ~half the steps) */
+    int32_t reserved;
     void*   peer_ctx;       /* vb_peer_create context: the camera pass runs FUSED with its cross-rank sum over
                              * NVLink peer memory (allreduce / allreduce_ctx are then used for the few other
                              * reductions only and may point at vb_peer_allreduce); NULL: separate collective */

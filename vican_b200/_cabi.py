@@ -40,7 +40,8 @@ class VbGraph(C.Structure):
 
 class VbSo3Options(C.Structure):
     _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP),
-                ("profile_events", I32), ("no_shortcut", I32), ("peer_ctx", VP)]
+                ("profile_events", I32), ("no_shortcut", I32), ("identity_start", I32), ("reserved", I32),
+                ("peer_ctx", VP)]
 
 
 class VbSo3Stats(C.Structure):

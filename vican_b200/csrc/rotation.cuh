@@ -35,6 +35,32 @@ __global__ void fill_identity_kernel(double* __restrict__ X, int64_t n) {
     L[0] = 1; L[1] = 0; L[2] = 0; L[3] = 0; L[4] = 1; L[5] = 0; L[6] = 0; L[7] = 0; L[8] = 1;
 }
 
+// start block of the first eigen-solve, step 1: X = E_0 (identity at the gauge camera, zero elsewhere)
+__global__ void fill_root_kernel(double* __restrict__ X, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = (i == 0) ? 1.0 : 0.0;
+    double* L = X + 9 * i;
+    L[0] = d; L[1] = 0; L[2] = 0; L[3] = 0; L[4] = d; L[5] = 0; L[6] = 0; L[7] = 0; L[8] = d;
+}
+
+// step 2: Y = P Lambda_T P^T E_0 holds, for every camera that shares a time node with the gauge camera, the
+// weighted sum of its relative rotations to it: X_c = project_SO3(Y_c) is a one-hop spanning estimate of the
+// solution (identity where nothing was seen).  The eigen-solve converges to the same invariant subspace from any
+// start; from this one it needs about half the steps it needs from identity blocks.
+__global__ void __launch_bounds__(NODE_THREADS) init_from_root_kernel(const double* __restrict__ Y, double* __restrict__ X, int64_t n_c) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_c) return;
+    double m[9], rot[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = Y[9 * c + i];
+    const double f2 = frob2_3(m);
+    if (f2 > 1e-200 && isfinite(f2)) node_factors(m, rot, nullptr, nullptr);
+    else { rot[0] = 1; rot[1] = 0; rot[2] = 0; rot[3] = 0; rot[4] = 1; rot[5] = 0; rot[6] = 0; rot[7] = 0; rot[8] = 1; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) X[9 * c + i] = rot[i];
+}
+
 // bipgo.py:295-297: r_c = project_SO3(V_c inv(V_0)); camera 0 is the gauge camera (first in the
 // reference's lexicographic node order -- the host assigns indices in that order).
 // r12 (optional): the same blocks in the padded gather layout (3 rows x 4 doubles) for the next time pass
@@ -290,7 +316,17 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     static const bool lob_timing = getenv("VICAN_B200_LOBPCG_TIMING") != nullptr;   // diagnostics: stage times of every step
 
     for (int outer = 0; outer < opt->maxiter; ++outer) {
-        if (outer == 0) VB_RC(time_pass(0, w.X, w.Wt));
+        if (outer == 0) {
+            if (opt->identity_start == 0) {   // one-hop spanning start (2 extra edge passes, see init_from_root_kernel)
+                fill_root_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, n_c);
+                VB_RC(time_pass(0, w.X, w.Wt));
+                VB_RC(cam_pass(w.Wt, w.Y));
+                init_from_root_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, w.X, n_c);
+                VB_KERNEL_CHECK();
+                S->kernel_launches += 2;
+            }
+            VB_RC(time_pass(0, w.X, w.Wt));
+        }
         VB_RC(cam_pass(w.Wt, w.Y));
         // A host-issued collective (NCCL hook without the fused peer path) also runs for the speculative camera
         // pass that follows a converged step and would sum the already summed Y once more: keep a copy for the

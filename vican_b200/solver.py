@@ -153,11 +153,15 @@ class DeviceGraph:
             self.tile_len = tl
             max_tiles = int(lib.vb_ingest_max_tiles(E, self.n_c, tl))
             e = lambda n, dt: torch.empty(n, dtype=dt, device=dev)  # noqa: E731
-            z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
-            # the edge passes stream blocks / indices with 16-byte granular bulk copies:
-            # 2 blocks / 8 indices of zero padding behind the arrays keep those reads in bounds
-            self._t_cam_pad, self._t_B_pad = z(E + 8, I32), z((E + 2, 9), F64)
-            self._c_time_pad, self._c_B_pad = z(E + 8, I32), z((E + 2, 9), F64)
+            # the edge passes stream blocks / indices with 16-byte granular bulk copies: 2 blocks / 8 indices
+            # of padding behind the arrays keep those reads in bounds.  Only the tail is cleared (the padding is
+            # staged but never consumed); zero-filling the whole arrays cost 7.6 GB of writes per ingestion.
+            self._t_cam_pad, self._t_B_pad = e(E + 8, I32), e((E + 2, 9), F64)
+            self._c_time_pad, self._c_B_pad = e(E + 8, I32), e((E + 2, 9), F64)
+            for pad_arr in (self._t_cam_pad, self._c_time_pad):
+                pad_arr[E:].zero_()
+            for pad_arr in (self._t_B_pad, self._c_B_pad):
+                pad_arr[E:].zero_()
             self.t_cam, self.t_B = self._t_cam_pad[:E], self._t_B_pad[:E]
             self.c_time, self.c_B = self._c_time_pad[:E], self._c_B_pad[:E]
             self.t_rowptr, self.t_time = e(self.n_t + 1, I32), e(E, I32)
@@ -213,9 +217,12 @@ class RotationResult:
 
 
 def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner: int = 200,
-                    comm: Optional[Comm] = None, profile_events: bool = False, shortcut: bool = True) -> RotationResult:
+                    comm: Optional[Comm] = None, profile_events: bool = False, shortcut: bool = True,
+                    spanning_start: bool = True) -> RotationResult:
     """``shortcut=False`` forces the primal multiply through its two edge passes in every outer
-    iteration (see ``vb_so3_stats.shortcut_outer``); the results agree to rounding."""
+    iteration (see ``vb_so3_stats.shortcut_outer``); ``spanning_start=False`` starts the first eigen-solve
+    from identity blocks instead of the one-hop estimate around the gauge camera.  Both only change the
+    work done, not the result (agreement to rounding / to the eigen-solver's tolerance)."""
     lib = _cabi.lib()
     dev = g.device
     with torch.cuda.device(dev):
@@ -226,7 +233,7 @@ def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner:
         fn, fctx = comm.reducer(lib, 9 * g.n_c) if comm is not None else (None, None)
         fused = comm.peer if (comm is not None and comm.peer is not None and 9 * g.n_c <= comm.peer_capacity) else None
         opt = VbSo3Options(int(maxiter), int(max_inner), float(tol), fn, fctx, 1 if profile_events else 0,
-                           0 if shortcut else 1, fused)
+                           0 if shortcut else 1, 0 if spanning_start else 1, 0, fused)
         stats = VbSo3Stats()
         rc = lib.vb_so3sync_run(C.byref(g.cgraph), C.byref(opt), _ptr(r_c), _ptr(r_t), _ptr(ws), wsb,
                                 C.byref(stats), _stream())
