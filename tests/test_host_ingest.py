@@ -167,3 +167,32 @@ def test_load_edges_reads_reference_pickles_without_the_reference_package(tmp_pa
         assert np.array_equal(out[k]["pose"].R(), src[k]["pose"]._R)
         assert np.array_equal(out[k]["pose"].t(), src[k]["pose"]._t)
         assert np.allclose(out[k]["pose"].inv().R(), src[k]["pose"]._R.T, atol=1e-6)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/vican"), reason="reference checkout not present (GPU box)")
+def test_load_edges_reads_a_pickle_written_with_the_real_reference_class(tmp_path):
+    """Same as above with the REAL ``vican.geometry.SE3`` (build container only): write with the reference
+    importable, read back in a subprocess-free way after hiding it again."""
+    import torch
+    sys.path.insert(0, "/root/reference")
+    try:
+        from vican.geometry import SE3 as RefSE3
+        g = _graph(0.0)
+        src = {(str(g.cam[e]), "%d_%d" % (g.time[e], g.marker[e])): {
+            "pose": RefSE3(R=g.R[e].copy(), t=g.t[e].copy()), "corners": np.zeros((4, 2)), "reprojected_err": 0.01,
+            "im_filename": "x"} for e in range(15)}
+        src[("0", "999_0")] = {"pose": RefSE3(pose=np.eye(4)), "corners": np.zeros((4, 2)), "reprojected_err": 0.0,
+                               "im_filename": "y"}
+        path = str(tmp_path / "cam_marker_edges.pt")
+        torch.save(src, path)
+        want = {k: (np.array(v["pose"].R()), np.array(v["pose"].t()), np.array(v["pose"].inv().R())) for k, v in src.items()}
+    finally:
+        sys.path.remove("/root/reference")
+        for m in [m for m in sys.modules if m == "vican" or m.startswith("vican.")]:
+            del sys.modules[m]
+    out = vio.load_edges(path)
+    assert list(out) == list(want)
+    for k, (R, t, Ri) in want.items():
+        assert type(out[k]["pose"]) is SE3
+        assert np.array_equal(out[k]["pose"].R(), R) and np.array_equal(out[k]["pose"].t(), t)
+        assert np.array_equal(out[k]["pose"].inv().R(), Ri)      # same float32 rounding as the reference container
