@@ -149,9 +149,16 @@ def lobpcg3(apply_L, prec, X0, tol, anorm, maxit=200, AX0=None):
     return X, th, napply, hist
 
 
-def so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-11, stats=None):
+def so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-11, stats=None, shortcut=True, spanning_start=True):
     """Device algorithm for bipgo.py:243-348 (matrix-free, LOBPCG).  Same return
-    convention as ``vican_oracle.so3sync``."""
+    convention as ``vican_oracle.so3sync``.
+
+    ``spanning_start``: the first eigen-solve starts from project_SO3((P Lambda_T P^T E_0)_c), the one-hop
+    estimate around the gauge camera, instead of identity blocks (csrc/rotation.cuh: init_from_root_kernel).
+    ``shortcut``: when an eigen-solve accepts its start block R (the previous r_c) without a single step, the
+    eigenvectors are V = R C, so V_c V_0^-1 = R_c R_0^T is already a rotation and the primal multiply
+    P Lambda_T P^T r_c equals Y R_0^T with Y = P Lambda_T P^T R computed for the eigen-residual: no edge passes
+    (csrc/rotation.cuh: so3sync_run).  ``stats.passes`` counts (time, camera) passes per outer iteration."""
     deg_t = np.zeros(n_t)
     np.add.at(deg_t, pt, a)
     deg_c = np.zeros(n_c)
@@ -160,33 +167,59 @@ def so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-11, stats=None):
     LamT = I3[None] / deg_t[:, None, None]
     LamC = I3[None] * deg_c[:, None, None]
     LamCinv = I3[None] / deg_c[:, None, None]
-    rng = np.random.default_rng(0)
     r_c = None
     r_t = None
+    Wt_next = None        # Lambda_T P^T r_c emitted by the dual update: the time half of the next L-apply
     for outer in range(maxiter):
+        npass = [0, 0]
+
+        def ppwr(X):      # P Lambda_T P^T X: one time pass + one camera pass
+            npass[0] += 1
+            npass[1] += 1
+            return pass_cam(pc, pt, B, LamT @ pass_time(pc, pt, B, X, n_t), n_c)
+
         def apply_L(Xf):
             X = Xf.reshape(n_c, 3, 3)
-            W = LamT @ pass_time(pc, pt, B, X, n_t)
-            return (LamC @ X - pass_cam(pc, pt, B, W, n_c)).reshape(3 * n_c, 3)
+            return (LamC @ X - ppwr(X)).reshape(3 * n_c, 3)
 
         def prec(Rf):
             return (LamCinv @ Rf.reshape(n_c, 3, 3)).reshape(3 * n_c, 3)
 
         anorm = 2.0 * np.abs(LamC).sum(axis=(1, 2)).max()
         if r_c is None:
-            X0 = np.tile(I3, (n_c, 1)) + 0.0 * rng.standard_normal((3 * n_c, 3))
+            if spanning_start:
+                E0 = np.zeros((n_c, 3, 3))
+                E0[0] = I3
+                Y0 = ppwr(E0)
+                X0b = np.tile(I3, (n_c, 1, 1))
+                seen = np.abs(Y0).sum(axis=(1, 2)) > 1e-200
+                X0b[seen] = svd_factors(Y0[seen])[0]
+            else:
+                X0b = np.tile(I3, (n_c, 1, 1))
+            Y = ppwr(X0b)
         else:
-            X0 = r_c.reshape(3 * n_c, 3)
-        V, th, napp, hist = lobpcg3(apply_L, prec, X0, tol, anorm)
+            X0b = r_c
+            npass[1] += 1                                   # camera pass only: the dual update emitted Wt
+            Y = pass_cam(pc, pt, B, Wt_next, n_c)
+        AX0 = (LamC @ X0b - Y).reshape(3 * n_c, 3)
+        V, th, napp, hist = lobpcg3(apply_L, prec, X0b.reshape(3 * n_c, 3), tol, anorm, AX0=AX0)
         if stats is not None:
-            stats.applies.append(napp)
+            stats.applies.append(napp + 1)
             stats.resid.append(hist[-1] / anorm)
             stats.theta.append(th.copy())
-        X = V @ np.linalg.inv(V[:3, :3])
-        r_c, _, _ = svd_factors(X.reshape(n_c, 3, 3))
-        W = LamT @ pass_time(pc, pt, B, r_c, n_t)
-        M = pass_cam(pc, pt, B, W, n_c)
+        if shortcut and r_c is not None and napp == 0:
+            M = Y @ X0b[0].T                                # (P Lambda_T P^T R) R_0^T
+        else:
+            X = V @ np.linalg.inv(V[:3, :3])
+            r_gauge, _, _ = svd_factors(X.reshape(n_c, 3, 3))
+            M = ppwr(r_gauge)
         r_c, LamC, LamCinv = svd_factors(M)
-        Y = pass_time(pc, pt, B, r_c, n_t)
-        r_t, _, LamT = svd_factors(Y)
+        npass[0] += 1
+        Yt = pass_time(pc, pt, B, r_c, n_t)
+        r_t, _, LamT = svd_factors(Yt)
+        Wt_next = LamT @ Yt
+        if stats is not None:
+            if not hasattr(stats, "passes"):
+                stats.passes = []
+            stats.passes.append(tuple(npass))
     return r_c, r_t
