@@ -15,8 +15,6 @@ import gc
 import pickle
 from typing import Callable, Dict, Iterable, Optional
 
-import numpy as np
-
 from .geometry import SE3
 
 __all__ = ["load_edges", "save_edges", "EdgeAccumulator"]

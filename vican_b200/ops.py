@@ -3,9 +3,6 @@ SO(3) projection and the SVD factors of the primal / dual updates.  Inputs may b
 or torch tensors; outputs are CUDA tensors."""
 from __future__ import annotations
 
-import ctypes as C
-
-import numpy as np
 import torch
 
 from . import _cabi
