@@ -32,3 +32,20 @@ def test_oracle_matches_reference_golden(name):
 
 def test_golden_set_not_empty():
     assert len(golden_names()) >= 8
+
+
+def test_float32_reference_run_is_within_float32_rounding_of_the_oracle():
+    """The notebook calls the solver with dtype=np.float32 (main.ipynb cell 7): the reference's float32 run
+    (tests/golden/make_golden_f32.py) stays within single-precision rounding of the fp64 restatement."""
+    import os
+    from util import GOLDEN_DIR
+    from vican_b200.geometry import geodesic_rad, rel_translation_err
+    g, params, filter_on, _ = load_golden("net_small_cg_it3")
+    z = np.load(os.path.join(GOLDEN_DIR, "f32_net_small_cg_it3.npz"))
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(filter_on)
+    out = orc.bipartite_se3sync_oracle(edges, constraints, nr, nt, ef, **params)
+    keys = [str(k) for k in z["out_keys"]]
+    assert geodesic_rad(np.stack([out[k][0] for k in keys]), z["out_R"]).max() < 5e-7
+    assert rel_translation_err(np.stack([out[k][1] for k in keys]), z["out_t"]).max() < 1e-5
+    assert str(z["R_dtype"]) == "float32" and str(z["t_dtype"]) == "float64"
