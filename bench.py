@@ -238,7 +238,7 @@ def main():
         st = res.rot.stats
         in_step["time"][0] += st.time_pass_ms; in_step["time"][1] += st.time_pass_timed
         in_step["cam"][0] += st.cam_pass_ms; in_step["cam"][1] += st.cam_pass_timed
-        launches += 13 + st.kernel_launches + 5 + 9 * res.trans.iters
+        launches += 13 + st.kernel_launches + 12 + 3 * (res.trans.iters + 8)
         loop_ms.append(res.phase_ms["rotation"])
     e1.record()
     torch.cuda.synchronize(); barrier()
@@ -267,7 +267,7 @@ def main():
     ptr, stream = solver._ptr, solver._stream
     kern = {}
     for name, fn in (("edge_pass_kernel<0> (time pass)", lambda: lib.vb_pass_time(C.byref(g.cgraph), 0, ptr(X), ptr(lamT), ptr(Wt), stream())),
-                     ("edge_pass_kernel<2> (camera pass)", lambda: lib.vb_pass_cam(C.byref(g.cgraph), ptr(Wt), ptr(Y), stream()))):
+                     ("edge_pass_kernel<3> + tile_combine (camera pass)", lambda: lib.vb_pass_cam(C.byref(g.cgraph), ptr(Wt), ptr(Y), stream()))):
         for _ in range(3):
             fn()
         reps = 20

@@ -50,9 +50,20 @@ typedef struct vb_graph {
     const double*  c_w;        /* [E] */
     const int32_t* tile_cam;   /* [n_tiles] */
     const int32_t* tile_start; /* [n_tiles] */
-    const int32_t* tile_end;   /* [n_tiles] */
+    const int32_t* tile_off;   /* [n_windows*n_c+1] first tile of every (window, camera) run */
+    double*        tile_part;  /* [n_tiles][9] scratch of the camera pass: per-tile sums, combined per camera in a
+                                * fixed order (no atomics: the pass is bitwise reproducible) */
     const double*  deg_t;      /* [n_t]  sum of k_r over the node's edges (bipgo.py:271) */
     const double*  deg_c;      /* [n_c]  sum of k_r over the camera's LOCAL edges (bipgo.py:275) */
+    /* Translation Laplacian J^T J (bipgo.py:471-477) in a sliced-ELL layout, both sides: slices of 8 rows,
+     * chunks of 4 columns = 32 slots (slot 4 j + s of chunk q = column 4 q + s of row j of the slice; padding:
+     * index -1, weight 0).  Built by vb_sell_count / vb_sell_fill; NULL until then (only vb_trans_cg needs it). */
+    const int32_t* st_ptr;     /* [ceil(n_t/8)+1] first chunk of each slice of time rows */
+    const int32_t* st_idx;     /* [32 * chunks_t] camera of the slot (ascending within a row) */
+    const double*  st_w;       /* [32 * chunks_t] sum k_t^2 of the pair */
+    const int32_t* sc_ptr;     /* [ceil(n_c/8)+1] camera rows */
+    const int32_t* sc_idx;     /* [32 * chunks_c] time node of the slot (ascending within a row) */
+    const double*  sc_w;       /* [32 * chunks_c] */
 } vb_graph;
 
 /* Optional cross-rank reduction hook (edge-sharded multi-GPU): called on `stream` after every
@@ -150,7 +161,8 @@ int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64
  * maps their positions to time-sorted edges, c_segptr [n_windows*n_c+1] delimits the run of every
  * (window, camera) -- per-camera reductions walk a camera's n_windows runs -- and the runs are cut
  * into tiles (runs of one camera, <= tile_len edges, contiguous: tile_start carries a
- * sentinel tile_start[n_tiles] = E).  tile arrays must hold vb_ingest_max_tiles + 1 entries.
+ * sentinel tile_start[n_tiles] = E; tile_off [n_windows*n_c+1] = first tile of every run).  tile_cam /
+ * tile_start must hold vb_ingest_max_tiles + 1 entries.
  * PADDING: t_B / c_B must be allocated for E + 2 blocks and t_cam / c_time for E + 8 indices
  * (the edge passes stream them with 16-byte granular bulk copies). */
 int64_t vb_ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len);
@@ -161,7 +173,7 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int64_t n_c, int64_t n_t, int64_t tile_len,
                     int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
                     int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
-                    int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_end,
+                    int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_off,
                     int64_t* h_n_tiles, double* deg_t, double* deg_c, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
@@ -171,8 +183,9 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
  * bytes, then padding up to one 128-byte line) so that one row is one 256-bit load and the three
  * rows of a block share an L1 line; vb_pad_blocks converts a compact [n][9] array.
  *   vb_pass_time: out12_t = [Lambda_T[t]] * sum_{e in t} B_e^T X12[c_e]  (mode 0 with lamT [n_t][9], mode 1 raw sum)
- *   vb_pass_cam : Y_c    += sum_{e in c} B_e W12[t_e]      (Y compact [n_c][9], zeroed by the caller;
- *                 g->c_B holds the blocks transposed, as vb_ingest_build writes them) */
+ *   vb_pass_cam : Y_c     = sum_{e in c} B_e W12[t_e]      (Y compact [n_c][9]; per-tile sums go to
+ *                 g->tile_part and are combined per camera in a fixed order; g->c_B holds the blocks
+ *                 transposed, as vb_ingest_build writes them) */
 int vb_gather_stride(void);
 int vb_pad_blocks(const double* src9, double* dst12, int64_t n, void* stream);
 int vb_pass_time(const vb_graph* g, int mode, const double* X12, const double* lamT, double* out12, void* stream);
@@ -201,13 +214,27 @@ int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair
                  const double* t_cm, const double* k_t, const double* marker_q, const double* r_c,
                  const double* r_t, const int32_t* t_time, double* pair_g,
                  double* d_sorted, double* rhs_c, double* rhs_t, void* stream);
+/* Sliced-ELL copy of the translation Laplacian for vb_trans_cg (see vb_graph).  vb_sell_count writes the slice
+ * pointers (st_ptr [ceil(n_t/8)+2], sc_ptr [ceil(n_c/8)+2]) and returns the chunk totals on the host
+ * (synchronises); the caller allocates 32 * chunks slots per side and vb_sell_fill fills them. */
+int64_t vb_sell_workspace_bytes(int64_t n_c, int64_t n_t);
+int vb_sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* h_chunks_t, int64_t* h_chunks_c,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+int vb_sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
+                 int32_t* sc_idx, double* sc_w, void* stream);
 int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t);
 /* Conjugate gradients on J^T J x = J^T t~ replaying scipy.sparse.linalg.cg as the reference
  * calls it (bipgo.py:477: x0 = 0, no preconditioner, rtol = 1e-5, atol = 0, maxiter = 10 * 3N,
- * ||r|| tested before each step).  jacobi != 0 switches to the Jacobi-preconditioned variant
- * (accurate mode; not the reference iteration).  x_c [n_c][3], x_t [n_t][3]. */
+ * ||r|| tested before each step), including the ARITHMETIC of its CSR mat-vec: every row of J^T J p is the
+ * left-to-right sum over ascending unknown index with separately rounded products (csrc/cg.cuh).
+ * unk_c [n_c] / unk_t [n_t]: index of every camera / time node in the reference's unknown order (bipgo.py:
+ * 420-430; it fixes where the diagonal entry sits inside a row); both NULL = cameras first, then time nodes.
+ * Node indices must ascend with the unknown index inside each class.  Deterministic (no atomics): bitwise
+ * reproducible run to run.  jacobi != 0 switches to the Jacobi-preconditioned variant (accurate mode; not
+ * the reference iteration).  x_c [n_c][3], x_t [n_t][3].  Needs g->st_* / g->sc_*. */
 int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t,
-                double rtol, int64_t maxiter, int jacobi, int32_t* h_iters, void* workspace,
+                double rtol, int64_t maxiter, int jacobi, const int32_t* unk_c, const int32_t* unk_t,
+                int32_t* h_iters, void* workspace,
                 int64_t workspace_bytes, vb_allreduce_fn allreduce, void* allreduce_ctx,
                 int owns_camera_diagonal /* 1 on a single GPU and on rank 0 of a sharded run */, void* stream);
 int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw);

@@ -105,7 +105,7 @@ def main_gpu():
         full = make_scaled_network(seed, n_c, n_t, d, 0, n_t, block=4000, device=dev)
         ref = solver.solve_arrays(full.cam, full.time, full.marker, full.R, full.t, full.k_r, full.k_t, I9, q0, n_c,
                                   n_t, maxiter, "conjugate_gradient")
-        from vican_b200.geometry import geodesic_rad, rel_translation_err
+        from util import geodesic_rad, rel_translation_err
         ec = geodesic_rad(res.Rw_c.cpu().numpy(), ref.Rw_c.cpu().numpy()).max()
         et = geodesic_rad(torch.cat(parts_R).cpu().numpy(), ref.Rw_t.cpu().numpy()).max()
         xc = rel_translation_err(res.x_c.cpu().numpy(), ref.x_c.cpu().numpy()).max()

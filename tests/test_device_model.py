@@ -7,7 +7,7 @@ import pytest
 from oracle import device_model as dm
 from oracle import vican_oracle as orc
 from vican_b200 import synthetic as syn
-from vican_b200.geometry import geodesic_rad
+from util import geodesic_rad
 
 
 def _pairs(seed, shape, outl=0.0):

@@ -13,7 +13,8 @@ torch = pytest.importorskip("torch")
 from oracle import device_model as dm            # noqa: E402
 from oracle import vican_oracle as orc           # noqa: E402
 from vican_b200 import synthetic as syn          # noqa: E402
-from vican_b200.geometry import SE3, geodesic_rad, rel_translation_err  # noqa: E402
+from vican_b200.geometry import SE3  # noqa: E402
+from util import geodesic_rad, rel_translation_err  # noqa: E402
 
 from util import ROT_TOL_RAD, TRANS_REL_TOL, callables, compare, golden_names, load_golden  # noqa: E402
 

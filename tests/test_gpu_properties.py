@@ -10,7 +10,8 @@ torch = pytest.importorskip("torch")
 
 from oracle import vican_oracle as orc           # noqa: E402
 from vican_b200 import synthetic as syn          # noqa: E402
-from vican_b200.geometry import SE3, geodesic_rad  # noqa: E402
+from vican_b200.geometry import SE3  # noqa: E402
+from util import geodesic_rad  # noqa: E402
 
 from util import ROT_TOL_RAD, TRANS_REL_TOL, callables, compare  # noqa: E402
 

@@ -26,13 +26,21 @@ def _same(a, b):
 
 
 def test_node_order_is_the_references_lexicographic_order():
-    """bipgo.py:225-229: nodes = np.unique(strings) -> '10' sorts before '2'."""
+    """bipgo.py:225-229: nodes = np.unique(strings) -> '10' sorts before '2'.  Time nodes follow the
+    order of the translation unknowns, np.unique over t+'_0' (bipgo.py:420-430: '10_0' < '1_0')."""
     g = _graph(0.0)
     edges, cons = syn.to_edge_dict(g, SE3)
     nr, nt, ef = syn.default_callables()
     tab = EdgeTable(edges, cons, nr, nt, ef)
     assert list(tab.cam_ids) == sorted({k[0] for k in edges})
-    assert list(tab.time_ids) == sorted({k[1].split("_")[0] for k in edges})
+    assert list(tab.time_ids) == sorted({k[1].split("_")[0] for k in edges}, key=lambda t: t + "_0")
+    assert list(tab.time_ids).index("10") < list(tab.time_ids).index("1")
+    # unknown_index() = position in np.unique over all node names together
+    unk_c, unk_t = tab.unknown_index()
+    names = np.unique(np.asarray(list(tab.cam_ids) + [t + "_0" for t in tab.time_ids]))
+    assert [names[i] for i in unk_c] == list(tab.cam_ids)
+    assert [names[i] for i in unk_t] == [t + "_0" for t in tab.time_ids]
+    assert np.all(np.diff(unk_c) > 0) and np.all(np.diff(unk_t) > 0)
     assert list(tab.cam_ids).index("10") < list(tab.cam_ids).index("2")
     # every detection is coded with the index of its own ids
     keys = list(edges.keys())

@@ -39,7 +39,7 @@ def test_float32_reference_run_is_within_float32_rounding_of_the_oracle():
     (tests/golden/make_golden_f32.py) stays within single-precision rounding of the fp64 restatement."""
     import os
     from util import GOLDEN_DIR
-    from vican_b200.geometry import geodesic_rad, rel_translation_err
+    from util import geodesic_rad, rel_translation_err
     g, params, filter_on, _ = load_golden("net_small_cg_it3")
     z = np.load(os.path.join(GOLDEN_DIR, "f32_net_small_cg_it3.npz"))
     edges, constraints = syn.to_edge_dict(g, SE3)

@@ -33,8 +33,9 @@ class VbGraph(C.Structure):
         ("n_c", I64), ("n_t", I64), ("n_edges", I64), ("n_tiles", I64), ("n_windows", I64),
         ("t_rowptr", VP), ("t_cam", VP), ("t_B", VP), ("t_w", VP),
         ("c_segptr", VP), ("c_order", VP), ("c_time", VP), ("c_B", VP), ("c_w", VP),
-        ("tile_cam", VP), ("tile_start", VP), ("tile_end", VP),
+        ("tile_cam", VP), ("tile_start", VP), ("tile_off", VP), ("tile_part", VP),
         ("deg_t", VP), ("deg_c", VP),
+        ("st_ptr", VP), ("st_idx", VP), ("st_w", VP), ("sc_ptr", VP), ("sc_idx", VP), ("sc_w", VP),
     ]
 
 
@@ -85,8 +86,11 @@ SIGNATURES = {
                                  C.POINTER(VbSo3Stats), VP]),
     "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "vb_trans_cg_workspace_bytes": (I64, [I64, I64]),
-    "vb_trans_cg": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, F64, I64, C.c_int, c_i32p, VP, I64, VP, VP, C.c_int,
-                              VP]),
+    "vb_sell_workspace_bytes": (I64, [I64, I64]),
+    "vb_sell_count": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, c_i64p, VP, I64, VP]),
+    "vb_sell_fill": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP]),
+    "vb_trans_cg": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, F64, I64, C.c_int, VP, VP, c_i32p, VP, I64, VP, VP,
+                              C.c_int, VP]),
     "vb_trans_lsqr_workspace_bytes": (I64, [I64, I64, I64]),
     "vb_trans_lsqr": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, I64, VP, VP, F64, F64, F64, I64,
                                 c_i32p, c_i32p, VP, I64, VP]),

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import gc
 import time as _time
+import warnings
 from typing import Callable, Dict, Optional
 
 import numpy as np
@@ -21,7 +22,7 @@ from . import solver as _solver
 from .geometry import SE3
 
 __all__ = ["bipartite_se3sync", "object_bipartite_se3sync", "large_bipartite_so3sync", "EdgeTable", "solve_table",
-           "last_info"]
+           "last_info", "EigenConvergenceWarning"]
 
 # diagnostics of the most recent call (iteration counts, Ritz values, timings)
 last_info: Dict[str, object] = {}
@@ -81,11 +82,17 @@ class EdgeTable:
             parts = s.split("_")                                             # bipgo.py:206-207
             constraints[parts[1]]                                            # KeyError like bipgo.py:209
             split[s] = (parts[0], parts[1])
-        # node order = np.unique over 'c'+id / 't'+timestamp strings (bipgo.py:225-229); the
-        # one-letter prefix does not change the order, so unique over the bare ids is the same.
+        # Camera order = np.unique over 'c'+id strings (bipgo.py:225-229; the one-letter prefix does not
+        # change the order): index 0 is the gauge camera.  Time nodes are labelled in the order of the
+        # TRANSLATION unknowns, np.unique over t+'_0' (bipgo.py:420-430), which differs from the
+        # rotation stage's np.unique over 't'+t when one timestamp is a prefix of another ('1_0' >
+        # '10_0' but 't1' < 't10').  The rotation stage does not depend on how time nodes are
+        # labelled; the replayed CSR product of the translation CG does (its row sums run over
+        # ascending unknown index, csrc/cg.cuh), so node indices ascend with the unknown index.
         # np.unique runs on the DISTINCT ids only; detections are coded through dictionaries.
         self.cam_ids = np.unique(np.asarray(list(dict.fromkeys(cams))))
-        self.time_ids = np.unique(np.asarray(list(dict.fromkeys(p[0] for p in split.values()))))
+        tids = np.unique(np.asarray([t + "_0" for t in dict.fromkeys(p[0] for p in split.values())]))
+        self.time_ids = np.asarray([t[:-2] for t in tids])
         self.marker_ids = sorted({p[1] for p in split.values()} | {self.root})
         cpos = {str(c): i for i, c in enumerate(self.cam_ids)}
         tpos = {str(t): i for i, t in enumerate(self.time_ids)}
@@ -95,9 +102,14 @@ class EdgeTable:
         self.cam_idx = np.fromiter(map(cpos.__getitem__, cams), dtype=np.int32, count=n)
         self.time_idx = np.fromiter(map(tcode.__getitem__, tm_keys), dtype=np.int32, count=n)
         self.marker_idx = np.fromiter(map(mcode.__getitem__, tm_keys), dtype=np.int32, count=n)
+        if isinstance(Rs, list) and len({r.dtype for r in Rs}) > 1:
+            # the float32 rounding of `k_r * pose.R()` is mirrored per CALL, not per detection
+            raise ValueError("detections mix float32 and float64 pose arrays; convert them to one dtype")
         R = np.array(Rs) if isinstance(Rs, list) else Rs                     # np.array: 2.5x faster than np.stack here
         # numpy evaluates `k_r * pose.R()` in float32 when the pose arrays are float32 (poses
-        # that went through SE3.inv(), geometry.py:209-211) and k_r is a Python float
+        # that went through SE3.inv(), geometry.py:209-211) and k_r is a Python float.  Only that first
+        # product is rounded here; the reference's float32 chain also rounds the two constraint products
+        # when the constraints are float32 arrays (deviation <= 1e-7 rad, tests/golden f32 case).
         self.round_kr_f32 = bool(R.dtype == np.float32 and not isinstance(kr[0], np.floating))
         self.R = R.astype(np.float64).reshape(-1, 9)
         self.t = (np.array(ts) if isinstance(ts, list) else ts).astype(np.float64).reshape(-1, 3)
@@ -114,6 +126,15 @@ class EdgeTable:
             q.append(np.asarray(r_0m, dtype=np.float64) @ np.asarray(t_m0, dtype=np.float64))
         self.marker_q = np.stack(q)
 
+    def unknown_index(self):
+        """(unk_c, unk_t): position of every camera / time node in the reference's unknown vector,
+        np.unique over camera ids and t+'_0' strings together (bipgo.py:420-430)."""
+        names = np.asarray(list(self.cam_ids) + [t + "_0" for t in self.time_ids])
+        order = np.argsort(names, kind="stable")
+        unk = np.empty(order.shape[0], dtype=np.int32)
+        unk[order] = np.arange(order.shape[0], dtype=np.int32)
+        return unk[:self.n_c], unk[self.n_c:]
+
     @property
     def n_c(self) -> int:
         return int(self.cam_ids.shape[0])
@@ -123,15 +144,31 @@ class EdgeTable:
         return int(self.time_ids.shape[0])
 
 
+class EigenConvergenceWarning(RuntimeWarning):
+    """The eigen-iteration of an outer iteration stopped at its step cap before reaching its
+    tolerance (the reference's ARPACK call raises ArpackNoConvergence in that situation)."""
+
+
 def _solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: Optional[str], mode: str = "parity",
-                 tol: float = 1e-13):
+                 tol: float = 1e-13, strict: bool = False):
     t0 = _time.perf_counter()
+    if tab.n_c < 3:
+        raise ValueError("the rotation stage needs at least 3 camera nodes (the reference asks ARPACK for 5 "
+                         "eigenpairs of a 3 n_c x 3 n_c matrix); got %d" % tab.n_c)
     g = _solver.DeviceGraph(tab.cam_idx, tab.time_idx, tab.marker_idx, tab.R, tab.k_r, tab.k_t, tab.markerC,
                             tab.n_c, tab.n_t, round_kr_f32=tab.round_kr_f32)
     rot = _solver.solve_rotations(g, maxiter, tol=tol)
+    if rot.status == 2 or rot.stats.stalled_outer > 0:
+        msg = ("eigen-iteration stopped at its step cap in %d of %d outer iterations (residual %.2e, scale %.2e): "
+               "the poses may be inaccurate (outliers / weak connectivity?)"
+               % (rot.stats.stalled_outer, maxiter, max(rot.stats.resid), rot.stats.anorm))
+        if strict:
+            raise _solver.ConvergenceError(msg)
+        warnings.warn(msg, EigenConvergenceWarning, stacklevel=3)
     tr = None
     if lsqr_solver is not None:
-        tr = _solver.solve_translations(g, rot, tab.t, tab.marker_q, lsqr_solver, mode=mode)
+        tr = _solver.solve_translations(g, rot, tab.t, tab.marker_q, lsqr_solver, mode=mode,
+                                        unknown_index=tab.unknown_index())
     torch.cuda.synchronize()
     last_info.clear()
     last_info.update(dict(
@@ -154,14 +191,14 @@ def large_bipartite_so3sync(src_edges: dict, constraints: dict, noise_model: Cal
     out = {}
     for i, c in enumerate(tab.cam_ids):                                      # bipgo.py:344-348
         out[c] = Rc[i]
-    for j, t in enumerate(tab.time_ids):
-        out[t + "_0"] = Rt[j]
+    for j in np.argsort(tab.time_ids, kind="stable"):                        # insertion order: np.unique('t' + t)
+        out[tab.time_ids[j] + "_0"] = Rt[j]
     return out
 
 
 def bipartite_se3sync(src_edges: dict, constraints: dict, noise_model_r: Callable, noise_model_t: Callable,
                       edge_filter: Callable, maxiter: int, lsqr_solver: str, dtype=np.float32,
-                      *, mode: str = "parity") -> dict:
+                      *, mode: str = "parity", strict: bool = False) -> dict:
     """SE(3) synchronisation in a bipartite camera / object-timestep graph with node
     constraints; same contract as ``vican/bipgo.py:353-490``.  Returns a dict with every camera
     id and every ``f"{t}_0"`` node mapped to an ``SE3`` pose wrt the world.
@@ -169,19 +206,22 @@ def bipartite_se3sync(src_edges: dict, constraints: dict, noise_model_r: Callabl
     The arithmetic is always fp64 on the device; ``dtype`` only selects the dtype of the returned
     rotation arrays (the reference's ``R`` follows ``dtype``, its ``t`` is float64).
     Raises ``ValueError`` for an unknown ``lsqr_solver`` (the reference falls through to a
-    NameError) and ``ConvergenceError`` (an ``AssertionError``) if CG does not converge."""
+    NameError) and ``ConvergenceError`` (an ``AssertionError``) if CG does not converge.  An
+    eigen-iteration that stops at its step cap emits ``EigenConvergenceWarning`` (``strict=True``:
+    raises ``ConvergenceError``, like ARPACK's ``ArpackNoConvergence`` in the reference)."""
     if lsqr_solver not in ("conjugate_gradient", "direct"):
         raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
     tab = EdgeTable(src_edges, constraints, noise_model_r, noise_model_t, edge_filter)
-    return solve_table(tab, maxiter, lsqr_solver, dtype=dtype, mode=mode)
+    return solve_table(tab, maxiter, lsqr_solver, dtype=dtype, mode=mode, strict=strict)
 
 
-def solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: str, dtype=np.float32, *, mode: str = "parity") -> dict:
+def solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: str, dtype=np.float32, *, mode: str = "parity",
+                strict: bool = False) -> dict:
     """``bipartite_se3sync`` from an already flattened ``EdgeTable`` (``EdgeTable.from_arrays``,
     ``io.EdgeAccumulator.table``): same result dictionary, no dictionary walk, no callables."""
     if lsqr_solver not in ("conjugate_gradient", "direct"):
         raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
-    _, rot, tr = _solve_table(tab, maxiter, lsqr_solver, mode=mode)
+    _, rot, tr = _solve_table(tab, maxiter, lsqr_solver, mode=mode, strict=strict)
     Rc, Rt = rot.world_rotations()
     Rc, Rt = Rc.cpu().numpy().astype(dtype), Rt.cpu().numpy().astype(dtype)
     xc, xt = tr.x_c.cpu().numpy(), tr.x_t.cpu().numpy()
@@ -200,7 +240,7 @@ def solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: str, dtype=np.float32
 
 def object_bipartite_se3sync(src_edges: dict, noise_model_r: Callable, noise_model_t: Callable,
                              edge_filter: Callable, maxiter: int, lsqr_solver: str, dtype=np.float32,
-                             *, mode: str = "parity") -> dict:
+                             *, mode: str = "parity", strict: bool = False) -> dict:
     """Object calibration (single object, moving camera); same contract as
     ``vican/bipgo.py:493-545``: markers take the camera role, timesteps the object role, every
     pose is inverted (through float32, as ``SE3.inv`` does) and only marker poses are returned."""
@@ -232,5 +272,5 @@ def object_bipartite_se3sync(src_edges: dict, noise_model_r: Callable, noise_mod
                                             "im_filename": v["im_filename"]}
     out = bipartite_se3sync(edges, constraints={root: SE3(pose=np.eye(4))}, noise_model_r=noise_model_r,
                             noise_model_t=noise_model_t, edge_filter=edge_filter, maxiter=maxiter,
-                            lsqr_solver=lsqr_solver, dtype=dtype, mode=mode)
+                            lsqr_solver=lsqr_solver, dtype=dtype, mode=mode, strict=strict)
     return {k: v for k, v in out.items() if "_" not in k}                    # bipgo.py:543

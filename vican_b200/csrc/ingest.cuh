@@ -140,16 +140,17 @@ __global__ void seg_sum_kernel(const int* __restrict__ ptr, const int* __restric
     if (lane == 0) deg[warp] = acc;
 }
 
-__global__ void tile_count_kernel(const int* __restrict__ colptr, int* __restrict__ cnt, int64_t n_c, int tile_len) {
+// entry n_seg is the sentinel of the exclusive scan (tile_off[n_seg] = number of tiles)
+__global__ void tile_count_kernel(const int* __restrict__ colptr, int* __restrict__ cnt, int64_t n_seg, int tile_len) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_c) return;
-    const int len = colptr[c + 1] - colptr[c];
+    if (c > n_seg) return;
+    const int len = c < n_seg ? colptr[c + 1] - colptr[c] : 0;
     cnt[c] = (len + tile_len - 1) / tile_len;
 }
 
+// tiles are contiguous: tile_start doubles as a segment pointer array (sentinel tile_start[n_tiles] = E)
 __global__ void tile_fill_kernel(const int* __restrict__ colptr, const int* __restrict__ off, int* __restrict__ tile_cam,
-                                 int* __restrict__ tile_start, int* __restrict__ tile_end, int64_t n_seg, int64_t n_c,
-                                 int tile_len) {
+                                 int* __restrict__ tile_start, int64_t n_seg, int64_t n_c, int tile_len) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_seg) return;
     const int s = colptr[c], e = colptr[c + 1];
@@ -157,8 +158,8 @@ __global__ void tile_fill_kernel(const int* __restrict__ colptr, const int* __re
     for (int b = s; b < e; b += tile_len, ++t) {
         tile_cam[t] = (int)(c % n_c);
         tile_start[t] = b;
-        tile_end[t] = (b + tile_len < e) ? b + tile_len : e;
     }
+    if (c == n_seg - 1) tile_start[off[n_seg]] = e;
 }
 
 // key = window(time) * n_c + cam: camera-pass order.  The input (aggregated pairs) is already

@@ -34,6 +34,7 @@
 #pragma once
 #include <stdlib.h>
 
+#include "../../include/vican_b200.h"
 #include "common.cuh"
 #include "peer.cuh"
 
@@ -163,7 +164,9 @@ __device__ __forceinline__ void item_fma(const Item& it, const double (&b)[5][3]
 
 // MODE 0: out_t = Lambda_T[t] * sum B^T X   (padded rows)   -- L-apply / primal multiply (bipgo.py:300)
 // (raw gather out_t = sum B^T X for the dual update, bipgo.py:318: MODE 0 with lamT == nullptr, i.e. Lambda_T = I)
-// MODE 2: Y_c  += sum over tile of B W      (compact 9, fp64 atomics per TILE, not per edge)
+// MODE 2: Y_c  += sum over tile of B W      (compact 9, fp64 atomics per TILE, not per edge: the fused multi-GPU pass)
+// MODE 3: part[tile] = sum over tile of B W (plain stores; tile_combine_kernel adds a camera's tiles in a fixed
+//         order: the single-GPU camera pass is bitwise reproducible and needs no zeroed accumulator)
 //
 // Per-warp software pipeline over work items (<= 50 edges of one segment):
 //   FMA(item k)  ->  TMA issue(item k+2)  ->  wait + loads(item k+1)  ->  epilogue(segment of k, if it ends)
@@ -277,8 +280,10 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
                         lamC[0] * scratch[j] + lamC[1] * scratch[3 + j] + lamC[2] * scratch[6 + j];
                 }
                 __syncwarp();
-            } else {
+            } else if (MODE == 2) {
                 if (holder) atomicAdd(out + 9 * (size_t)__ldg(seg_node + i0.seg) + vidx, tot);
+            } else {
+                if (holder) out[9 * (size_t)i0.seg + vidx] = tot;
             }
 #pragma unroll
             for (int i = 0; i < 9; ++i) acc[i] = 0.0;
@@ -316,6 +321,22 @@ edge_pass_fused_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ 
     edge_pass_body<2>(seg_ptr, seg_node, idx, B, G, nullptr, mine, n_seg);
     peer_publish(pd, epoch);
     peer_reduce(pd, epoch, Y, n_y);
+}
+
+// Y_c = sum of the camera's per-tile sums, windows ascending, tiles ascending inside a run (fixed order)
+__global__ void tile_combine_kernel(const double* __restrict__ part, const int* __restrict__ tile_off, int64_t n_win, int64_t n_c,
+                                    double* __restrict__ Y, const double* __restrict__ skip_flag) {
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * n_c) return;
+    const int64_t c = i / 9;
+    const int k = (int)(i - 9 * c);
+    double acc = 0.0;
+    for (int64_t w = 0; w < n_win; ++w) {
+        const int t0 = __ldg(tile_off + w * n_c + c), t1 = __ldg(tile_off + w * n_c + c + 1);
+        for (int t = t0; t < t1; ++t) acc += part[9 * (size_t)t + k];
+    }
+    Y[i] = acc;
 }
 
 // compact [n][9] -> padded [n][GSTRIDE] node blocks (the gather source layout)
@@ -390,11 +411,15 @@ inline int launch_pass_time(int mode, const int* rowptr, const int* cam, const d
 }
 
 // tile_start carries a sentinel: tile_start[n_tiles] = E (tiles are contiguous).  W12 padded, Y compact.
-inline int launch_pass_cam(const int* tile_cam, const int* tile_start, const int* tidx, const double* B,
-                           const double* W12, double* Y, int64_t n_tiles, cudaStream_t st,
-                           const double* skip_flag = nullptr) {
-    if (n_tiles <= 0) return 0;
-    return launch_edge_pass<2>(tile_start, tile_cam, tidx, B, W12, nullptr, Y, n_tiles, st, skip_flag);
+// Two launches: per-tile sums into g->tile_part, then the per-camera combine (Y needs no zeroing).
+inline int launch_pass_cam(const vb_graph* g, const double* W12, double* Y, cudaStream_t st, const double* skip_flag = nullptr) {
+    if (g->n_tiles > 0) {
+        int rc = launch_edge_pass<3>(g->tile_start, g->tile_cam, g->c_time, g->c_B, W12, nullptr, g->tile_part, g->n_tiles, st, skip_flag);
+        if (rc) return rc;
+    }
+    tile_combine_kernel<<<(int)((9 * g->n_c + 255) / 256), 256, 0, st>>>(g->tile_part, g->tile_off, g->n_windows, g->n_c, Y, skip_flag);
+    VB_KERNEL_CHECK();
+    return 0;
 }
 
 }  // namespace vb

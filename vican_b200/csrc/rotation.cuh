@@ -283,11 +283,9 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
             last_cam_slot = slot;
             return rc;
         }
-        if (skip == nullptr) VB_CHECK(cudaMemsetAsync(Y, 0, cbytes, st));
-        else { cond_zero_kernel<<<node_grid(9 * n_c), NODE_THREADS, 0, st>>>(Y, 9 * n_c, skip); S->kernel_launches++; }
-        S->cam_passes++; S->kernel_launches++;
+        S->cam_passes++; S->kernel_launches += 2;
         const int slot = prof_begin(1);
-        int rc = launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, Wt, Y, g->n_tiles, st, skip);
+        int rc = launch_pass_cam(g, Wt, Y, st, skip);   // per-tile sums + fixed-order combine: no zeroing, no atomics
         prof_end(slot);
         last_cam_slot = slot;
         if (rc) return rc;
@@ -378,7 +376,7 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
             }
             if (hs[SM_CONV] != 0.0) {
                 if (speculated) {
-                    S->time_passes--; S->cam_passes--; S->lobpcg_steps--; S->kernel_launches -= 4;
+                    S->time_passes--; S->cam_passes--; S->lobpcg_steps--; S->kernel_launches -= (opt->peer_ctx != nullptr) ? 3 : 4;
                     if (last_time_slot >= 0) prof_kind[last_time_slot] = -1;
                     if (last_cam_slot >= 0) prof_kind[last_cam_slot] = -1;
                 }

@@ -1,6 +1,7 @@
 // C ABI of the vican_b200 CUDA extension (see include/vican_b200.h).  sm_100a only.
 #include "../../include/vican_b200.h"
 
+#include "cg.cuh"
 #include "common.cuh"
 #include "evaluate.cuh"
 #include "ingest.cuh"
@@ -167,7 +168,7 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     const int32_t* raw_pair, int64_t n_pairs, int64_t n_c, int64_t n_t, int64_t tile_len,
                     int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
                     int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
-                    int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_end, int64_t* h_n_tiles, double* deg_t,
+                    int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_off, int64_t* h_n_tiles, double* deg_t,
                     double* deg_c, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_raw <= 0 || n_pairs <= 0 || tile_len <= 0) return VB_STATUS_BAD_ARGUMENT;
@@ -192,19 +193,15 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.tmp_a, nullptr, c_segptr, E, n_seg);
     cam_runs_sum_kernel<<<ing_grid(n_c * 32), ING_THREADS, 0, st>>>(c_segptr, n_win, n_c, c_order, t_a, deg_c);
     gather_cam_sorted_kernel<<<ing_grid(9 * E), ING_THREADS, 0, st>>>(c_order, t_time, t_B, t_w, c_time, c_B, c_w, E);
-    tile_count_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(c_segptr, w.tmp_c, n_seg, (int)tile_len);
+    tile_count_kernel<<<ing_grid(n_seg + 1), ING_THREADS, 0, st>>>(c_segptr, w.tmp_c, n_seg, (int)tile_len);
     tb = w.cub_bytes;
-    VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.tmp_c, w.tmp_d, (int)n_seg, st));
-    tile_fill_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(c_segptr, w.tmp_d, tile_cam, tile_start, tile_end, n_seg, n_c, (int)tile_len);
+    VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.tmp_c, tile_off, (int)(n_seg + 1), st));
+    tile_fill_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(c_segptr, tile_off, tile_cam, tile_start, n_seg, n_c, (int)tile_len);
     VB_KERNEL_CHECK();
-    int last_off = 0, last_cnt = 0;
-    VB_CHECK(cudaMemcpyAsync(&last_off, w.tmp_d + (n_seg - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CHECK(cudaMemcpyAsync(&last_cnt, w.tmp_c + (n_seg - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    int last_off = 0;
+    VB_CHECK(cudaMemcpyAsync(&last_off, tile_off + n_seg, sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CHECK(cudaStreamSynchronize(st));
-    const int64_t n_tiles = (int64_t)last_off + last_cnt;
-    const int e32 = (int)E;   // sentinel: tiles are contiguous, tile_start doubles as a segment pointer array
-    VB_CHECK(cudaMemcpyAsync(tile_start + n_tiles, &e32, sizeof(int), cudaMemcpyHostToDevice, st));
-    VB_CHECK(cudaStreamSynchronize(st));
+    const int64_t n_tiles = (int64_t)last_off;
     *h_n_tiles = n_tiles;
     return 0;
 }
@@ -215,7 +212,7 @@ int vb_pass_time(const vb_graph* g, int mode, const double* X, const double* lam
 }
 
 int vb_pass_cam(const vb_graph* g, const double* W, double* Y, void* stream) {
-    return launch_pass_cam(g->tile_cam, g->tile_start, g->c_time, g->c_B, W, Y, g->n_tiles, (cudaStream_t)stream);
+    return launch_pass_cam(g, W, Y, (cudaStream_t)stream);
 }
 
 int vb_pad_blocks(const double* src9, double* dst12, int64_t n, void* stream) {
@@ -269,11 +266,24 @@ int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair
 
 int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_cg(nullptr, n_c, n_t).bytes; }
 
+int64_t vb_sell_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_sell(nullptr, n_c, n_t).bytes; }
+
+int vb_sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* h_chunks_t, int64_t* h_chunks_c,
+                  void* workspace, int64_t workspace_bytes, void* stream) {
+    return sell_count(g, st_ptr, sc_ptr, h_chunks_t, h_chunks_c, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vb_sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
+                 int32_t* sc_idx, double* sc_w, void* stream) {
+    return sell_fill(g, st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w, (cudaStream_t)stream);
+}
+
 int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t, double rtol,
-                int64_t maxiter, int jacobi, int32_t* h_iters, void* workspace, int64_t workspace_bytes,
-                vb_allreduce_fn allreduce, void* allreduce_ctx, int owns_camera_diagonal, void* stream) {
-    return trans_cg(g, rhs_c, rhs_t, x_c, x_t, rtol, maxiter, jacobi, h_iters, workspace, workspace_bytes, allreduce,
-                    allreduce_ctx, owns_camera_diagonal, (cudaStream_t)stream);
+                int64_t maxiter, int jacobi, const int32_t* unk_c, const int32_t* unk_t, int32_t* h_iters, void* workspace,
+                int64_t workspace_bytes, vb_allreduce_fn allreduce, void* allreduce_ctx, int owns_camera_diagonal,
+                void* stream) {
+    return trans_cg(g, rhs_c, rhs_t, x_c, x_t, rtol, maxiter, jacobi, unk_c, unk_t, h_iters, workspace, workspace_bytes,
+                    allreduce, allreduce_ctx, owns_camera_diagonal, (cudaStream_t)stream);
 }
 
 int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw) {

@@ -75,26 +75,33 @@ class EdgeAccumulator:
         self.marker_ids = None if marker_ids is None else set(marker_ids)     # cam.py:263 id whitelist
         self._cams, self._tm, self._R, self._t, self._kr, self._kt = [], [], [], [], [], []
         self._seen: Dict[tuple, int] = {}
+        self._dead = set()              # positions whose key was later re-detected and then filtered out
         self.n_dropped = 0
 
     def __len__(self) -> int:
-        return len(self._cams)
+        return len(self._cams) - len(self._dead)
 
     def add(self, detections: Optional[dict]) -> int:
         """Returns the number of detections kept from this chunk.  A key seen before replaces the
-        older detection (dictionary-merge semantics of cam.py:263)."""
+        older detection (dictionary-merge semantics of cam.py:263) -- also when the newer detection
+        fails ``edge_filter``: the merged dictionary would hold the newer one, which the solver then
+        filters out, so the older record is retired."""
         if not detections:
             return 0
         kept = 0
         for key, v in detections.items():
             if self.marker_ids is not None and key[-1].split("_")[-1] not in self.marker_ids:
                 continue
+            pos = self._seen.get(key)
             if not self.edge_filter(v):
                 self.n_dropped += 1
+                if pos is not None:
+                    self._dead.add(pos)
                 continue
             pose = v["pose"]
             rec = (key[0], key[1], pose.R(), pose.t(), self.noise_model_r(v), self.noise_model_t(v))
-            pos = self._seen.get(key)
+            if pos is not None:
+                self._dead.discard(pos)
             if pos is None:
                 self._seen[key] = len(self._cams)
                 for lst, x in zip((self._cams, self._tm, self._R, self._t, self._kr, self._kt), rec):
@@ -108,5 +115,9 @@ class EdgeAccumulator:
     def table(self, constraints: dict):
         from .bipgo import EdgeTable
         tab = EdgeTable.__new__(EdgeTable)
-        tab._assemble(self._cams, self._tm, list(self._R), list(self._t), self._kr, self._kt, constraints)
+        cols = (self._cams, self._tm, self._R, self._t, self._kr, self._kt)
+        if self._dead:
+            cols = tuple([x for i, x in enumerate(col) if i not in self._dead] for col in cols)
+        tab._assemble(list(cols[0]), list(cols[1]), list(cols[2]), list(cols[3]), list(cols[4]), list(cols[5]),
+                      constraints)
         return tab

@@ -170,8 +170,8 @@ class DeviceGraph:
             self.n_windows = int(lib.vb_ingest_windows(E, self.n_c, tl))
             self.c_segptr = e(self.n_windows * self.n_c + 1, I32)
             self.c_w, self.c_order = e(E, F64), e(E, I32)
-            self.tile_cam, self.tile_start, self.tile_end = (e(max_tiles + 1, I32), e(max_tiles + 1, I32),
-                                                             e(max_tiles + 1, I32))
+            self.tile_cam, self.tile_start = e(max_tiles + 1, I32), e(max_tiles + 1, I32)
+            self.tile_off = e(self.n_windows * self.n_c + 1, I32)
             self.deg_t, self.deg_c = e(self.n_t, F64), e(self.n_c, F64)
             ntiles = C.c_int64(0)
             check(lib.vb_ingest_build(
@@ -181,17 +181,47 @@ class DeviceGraph:
                 _ptr(self.t_a), _ptr(self.t_w), _ptr(self.pair_start), _ptr(self.c_segptr), _ptr(self.c_time),
                 _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_order), _ptr(self.tile_cam),
                 _ptr(self.tile_start),
-                _ptr(self.tile_end), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c), _ptr(ws), wsb, _stream()),
+                _ptr(self.tile_off), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c), _ptr(ws), wsb, _stream()),
                 "vb_ingest_build")
             self.n_tiles = int(ntiles.value)
+            self.tile_part = e((max(self.n_tiles, 1), 9), F64)      # camera-pass scratch (per-tile sums)
         del ws, R
         self.cgraph = VbGraph(
             self.n_c, self.n_t, E, self.n_tiles, self.n_windows,
             self.t_rowptr.data_ptr(), self.t_cam.data_ptr(), self.t_B.data_ptr(), self.t_w.data_ptr(),
             self.c_segptr.data_ptr(), self.c_order.data_ptr(), self.c_time.data_ptr(), self.c_B.data_ptr(),
             self.c_w.data_ptr(),
-            self.tile_cam.data_ptr(), self.tile_start.data_ptr(), self.tile_end.data_ptr(),
-            self.deg_t.data_ptr(), self.deg_c.data_ptr())
+            self.tile_cam.data_ptr(), self.tile_start.data_ptr(), self.tile_off.data_ptr(), self.tile_part.data_ptr(),
+            self.deg_t.data_ptr(), self.deg_c.data_ptr(), 0, 0, 0, 0, 0, 0)
+        self._sell = None
+
+    def ensure_sell(self):
+        """Sliced-ELL copy of the translation Laplacian (both sides), built on first use by the
+        conjugate-gradient solver (csrc/cg.cuh): 12 bytes per stored slot and side."""
+        if self._sell is not None:
+            return
+        lib = _cabi.lib()
+        dev = self.device
+        with torch.cuda.device(dev):
+            ns_t, ns_c = (self.n_t + 7) // 8, (self.n_c + 7) // 8
+            st_ptr = torch.empty(ns_t + 2, dtype=I32, device=dev)
+            sc_ptr = torch.empty(ns_c + 2, dtype=I32, device=dev)
+            wsb = int(lib.vb_sell_workspace_bytes(self.n_c, self.n_t))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            ct, cc = C.c_int64(0), C.c_int64(0)
+            check(lib.vb_sell_count(C.byref(self.cgraph), _ptr(st_ptr), _ptr(sc_ptr), C.byref(ct), C.byref(cc),
+                                    _ptr(ws), wsb, _stream()), "vb_sell_count")
+            st_idx = torch.empty(32 * max(int(ct.value), 1), dtype=I32, device=dev)
+            st_w = torch.empty(32 * max(int(ct.value), 1), dtype=F64, device=dev)
+            sc_idx = torch.empty(32 * max(int(cc.value), 1), dtype=I32, device=dev)
+            sc_w = torch.empty(32 * max(int(cc.value), 1), dtype=F64, device=dev)
+            check(lib.vb_sell_fill(C.byref(self.cgraph), _ptr(st_ptr), _ptr(st_idx), _ptr(st_w), _ptr(sc_ptr),
+                                   _ptr(sc_idx), _ptr(sc_w), _stream()), "vb_sell_fill")
+        self._sell = (st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w)
+        self.sell_chunks = (int(ct.value), int(cc.value))
+        g = self.cgraph
+        g.st_ptr, g.st_idx, g.st_w = st_ptr.data_ptr(), st_idx.data_ptr(), st_w.data_ptr()
+        g.sc_ptr, g.sc_idx, g.sc_w = sc_ptr.data_ptr(), sc_idx.data_ptr(), sc_w.data_ptr()
 
     # ---- algorithmic bytes of one edge pass (SURVEY.md 8d: 76 B / edge + node traffic) ----
     def pass_bytes(self, kind: str) -> int:
@@ -199,7 +229,7 @@ class DeviceGraph:
         if kind == "time":     # blocks + cam index, row pointers, Lambda_T read, W write (padded), X gather source
             return 76 * E + 4 * (n_t + 1) + 72 * n_t + 96 * n_t + 96 * n_c
         if kind == "cam":      # blocks + time index, tile table, W gather source (padded), Y accumulate
-            return 76 * E + 8 * self.n_tiles + 96 * n_t + 2 * 72 * n_c
+            return 76 * E + (8 + 2 * 72) * self.n_tiles + 96 * n_t + 72 * n_c
         raise ValueError(kind)
 
 
@@ -225,6 +255,8 @@ def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner:
     work done, not the result (agreement to rounding / to the eigen-solver's tolerance)."""
     lib = _cabi.lib()
     dev = g.device
+    if g.n_c < 3:
+        raise ValueError("the rotation stage needs at least 3 camera nodes (got %d)" % g.n_c)
     with torch.cuda.device(dev):
         wsb = int(lib.vb_so3sync_workspace_bytes(g.n_c, g.n_t))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -250,13 +282,16 @@ class TranslationResult:
 
 
 def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr_solver: str,
-                       mode: str = "parity", comm: Optional[Comm] = None) -> TranslationResult:
+                       mode: str = "parity", comm: Optional[Comm] = None, unknown_index=None) -> TranslationResult:
     """``lsqr_solver``: "conjugate_gradient" | "direct" (reference names, bipgo.py:476-480).
     ``mode``: "parity" replays scipy's truncated iterations (what the reference returns);
     "accurate" returns the minimum-norm minimiser itself (up to ~4e-3 away from the reference's
     truncated CG answer -- SURVEY.md 7.3-1): Jacobi-preconditioned CG to 1e-12 for
     "conjugate_gradient", a dense Cholesky of the camera Schur complement for "direct"
-    (single GPU, n_c <= SCHUR_MAX_CAMERAS; larger or sharded graphs use the PCG)."""
+    (single GPU, n_c <= SCHUR_MAX_CAMERAS; larger or sharded graphs use the PCG).
+    ``unknown_index`` = (unk_c [n_c], unk_t [n_t]): position of every camera / time node in the
+    reference's unknown vector (bipgo.py:420-430); it fixes where the diagonal entry sits in the
+    row sums of the replayed CSR product.  None: cameras first, then time nodes."""
     if lsqr_solver not in ("conjugate_gradient", "direct"):
         raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
     lib = _cabi.lib()
@@ -306,9 +341,13 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
             jacobi = 1 if mode == "accurate" else 0
             rtol = 1e-12 if mode == "accurate" else 1e-5
             fn, fctx = comm.reducer(lib, 3 * g.n_c + 8) if comm is not None else (None, None)
+            g.ensure_sell()
+            unk_c = unk_t = None
+            if unknown_index is not None:
+                unk_c, unk_t = (_dev(u, I32, dev) for u in unknown_index)
             rc = lib.vb_trans_cg(C.byref(g.cgraph), _ptr(rhs_c), _ptr(rhs_t), _ptr(x_c), _ptr(x_t), rtol,
-                                 10 * n_unknowns, jacobi, C.byref(iters), _ptr(ws), wsb, fn, fctx,
-                                 1 if (comm is None or comm.rank == 0) else 0, _stream())
+                                 10 * n_unknowns, jacobi, _ptr(unk_c), _ptr(unk_t), C.byref(iters), _ptr(ws), wsb,
+                                 fn, fctx, 1 if (comm is None or comm.rank == 0) else 0, _stream())
             if rc == 1:
                 raise ConvergenceError("conjugate gradient did not converge (reference: assert exit_code == 0)")
             check(rc, "vb_trans_cg")
@@ -330,9 +369,14 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
 _PINNED_OUT = {}
 
 
-def _to_pinned_host(name: str, t: torch.Tensor) -> torch.Tensor:
-    """Device -> host copy into a cached PINNED buffer (pageable destinations run at a few GB/s).
-    The buffer is reused by the next call with the same name and shape."""
+def _to_pinned_host(name: str, t: torch.Tensor, reuse: bool) -> torch.Tensor:
+    """Device -> host copy into a PINNED buffer (pageable destinations run at a few GB/s).  With
+    ``reuse`` the buffer is cached by (name, shape) and OVERWRITTEN by the next call with the same
+    shapes (results of an earlier call alias it); otherwise every call gets fresh buffers."""
+    if not reuse:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        return buf
     key = (name, tuple(t.shape), t.dtype)
     buf = _PINNED_OUT.get(key)
     if buf is None:
@@ -357,12 +401,14 @@ class SolveResult:
 def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int, n_t: int, maxiter: int,
                  lsqr_solver: str = "conjugate_gradient", mode: str = "parity", tol: float = 1e-13,
                  comm: Optional[Comm] = None, round_kr_f32: bool = False, to_host: bool = False,
-                 graph: Optional[DeviceGraph] = None, profile_events: bool = False) -> SolveResult:
+                 graph: Optional[DeviceGraph] = None, profile_events: bool = False,
+                 reuse_host_buffers: bool = False) -> SolveResult:
     """Array fast path of ``bipartite_se3sync`` (no dicts, no Python callables): raw detections
     as arrays (numpy / pinned host tensors / CUDA tensors) with pre-evaluated weights
     ``k_r = noise_model_r(e)``, ``k_t = noise_model_t(e)`` and already filtered by
     ``edge_filter``; node indices dense and in the caller's order (index 0 = gauge camera).
-    With ``to_host`` the results are copied back to (pinned) host memory."""
+    With ``to_host`` the results are copied back to pinned host memory (``reuse_host_buffers``: into
+    buffers cached across calls -- a later call with the same shapes overwrites them)."""
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record()
     upload = None
@@ -380,7 +426,7 @@ def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int,
     Rw_c, Rw_t = rot.world_rotations()
     x_c, x_t = tr.x_c, tr.x_t
     if to_host:
-        Rw_c, Rw_t, x_c, x_t = (_to_pinned_host(n, v) for n, v in
+        Rw_c, Rw_t, x_c, x_t = (_to_pinned_host(n, v, reuse_host_buffers) for n, v in
                                 (("Rw_c", Rw_c), ("Rw_t", Rw_t), ("x_c", x_c), ("x_t", x_t)))
     ev[3].record()
     torch.cuda.synchronize()
