@@ -217,7 +217,7 @@ def main():
     def one_solve(src=det, to_host=False, profile_events=False):
         return solver.solve_arrays(src.cam, src.time, src.marker, src.R, src.t, src.k_r, src.k_t, markerC, marker_q,
                                    n_c, src.n_t, maxiter, "conjugate_gradient", comm=comm, to_host=to_host,
-                                   profile_events=profile_events)
+                                   profile_events=profile_events, reuse_host_buffers=to_host)
 
     # ---- device-resident timing: W warm-up, K timed steps, barrier + synchronize on both sides
     res = None

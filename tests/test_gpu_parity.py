@@ -122,10 +122,16 @@ def test_ingestion_matches_oracle_aggregation(cuda, shape, shuffle):
     assert np.abs(dg.deg_c.cpu().numpy() - deg_c).max() < 1e-11
     # tiles cover every camera-pass edge exactly once, one camera per tile, contiguous + sentinel
     nt = dg.n_tiles
-    tc, ts, te = (x.cpu().numpy()[:nt] for x in (dg.tile_cam, dg.tile_start, dg.tile_end))
+    tc = dg.tile_cam.cpu().numpy()[:nt]
+    tsent = dg.tile_start.cpu().numpy()[:nt + 1]          # contiguous tiles + sentinel
+    ts, te = tsent[:-1], tsent[1:]
     assert np.all(te > ts) and np.all(te - ts <= dg.tile_len)
-    assert ts[0] == 0 and te[-1] == dg.n_edges and np.all(ts[1:] == te[:-1])
-    assert int(dg.tile_start.cpu().numpy()[nt]) == dg.n_edges
+    assert ts[0] == 0 and te[-1] == dg.n_edges
+    # tile_off: first tile of every (window, camera) run -- the fixed order of the per-camera combine
+    toff = dg.tile_off.cpu().numpy()
+    assert toff.shape[0] == dg.n_windows * a["n_c"] + 1 and toff[0] == 0 and toff[-1] == nt and np.all(np.diff(toff) >= 0)
+    for seg in range(dg.n_windows * a["n_c"]):
+        assert np.all(tc[toff[seg]:toff[seg + 1]] == seg % a["n_c"])
     cam_of_pos = pc[order][cord]
     for k in range(nt):
         assert np.all(cam_of_pos[ts[k]:te[k]] == tc[k])

@@ -243,9 +243,9 @@ __device__ __forceinline__ void cg_top(double* sc, double rtol, int first) {
 
 // Block sum of N per-thread values into row blockIdx.x of the partial table, then a ticket: returns
 // true in every thread of the LAST block to arrive (all rows are then visible to it).
-template <int N>
+template <int N, int WARPS = CG_WARPS>
 __device__ __forceinline__ bool cg_block_partial(const double (&v)[N], double* tab, unsigned* ticket) {
-    __shared__ double sm[N][CG_WARPS];
+    __shared__ double sm[N][WARPS];
     __shared__ bool last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -257,7 +257,7 @@ __device__ __forceinline__ bool cg_block_partial(const double (&v)[N], double* t
     if (threadIdx.x < N) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < CG_WARPS; ++w) s += sm[threadIdx.x][w];
+        for (int w = 0; w < WARPS; ++w) s += sm[threadIdx.x][w];
         tab[(size_t)blockIdx.x * N + threadIdx.x] = s;
     }
     __threadfence();
@@ -269,12 +269,12 @@ __device__ __forceinline__ bool cg_block_partial(const double (&v)[N], double* t
 }
 
 // fixed-order sum of component n of the table rows [b0, b1), by a whole block; result in every thread
-template <int N>
+template <int N, int THREADS = CG_THREADS>
 __device__ __forceinline__ double cg_table_sum(const double* tab, int n, int b0, int b1) {
-    __shared__ double sm[CG_WARPS];
+    __shared__ double sm[THREADS / 32];
     __shared__ double tot;
     double s = 0.0;
-    for (int b = b0 + (int)threadIdx.x; b < b1; b += CG_THREADS) s += __ldcg(tab + (size_t)b * N + n);
+    for (int b = b0 + (int)threadIdx.x; b < b1; b += THREADS) s += __ldcg(tab + (size_t)b * N + n);
     s = warp_sum(s);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -282,7 +282,7 @@ __device__ __forceinline__ double cg_table_sum(const double* tab, int n, int b0,
     if (threadIdx.x == 0) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < CG_WARPS; ++w) t += sm[w];
+        for (int w = 0; w < THREADS / 32; ++w) t += sm[w];
         tot = t;
     }
     __syncthreads();
@@ -406,20 +406,27 @@ __global__ void __launch_bounds__(1024) cg_alpha_multi_kernel(const double* __re
 }
 
 // ------------------------------------------------------------------------------- mat-vec
+// One side of the bipartite Laplacian in the sliced-ELL layout, as seen by the mat-vec.
+struct SellSide {
+    const int *ptr, *idx; const double* w; int64_t n_rows, n_slices;
+    const double *p_other, *p_self;   // padded [n][4]: gather source (far endpoint) and the rows' own entries
+    const double* dg;                 // weighted degrees (the diagonal of J^T J)
+    const int* ins;                   // position of the diagonal term in the row's sorted order (nullptr: ins_default)
+    int ins_default, add_diag;
+    double* q;                        // [n][3]; diag mode: [n] row sums of the weights
+};
+
 struct CgMv {
-    const int *st_ptr, *st_idx; const double* st_w; int64_t n_t, ns_t;
-    const int *sc_ptr, *sc_idx; const double* sc_w; int64_t n_c, ns_c;
-    const double *p_c, *p_t;          // padded [n][4]
-    const double *dg_c, *dg_t;
-    const int *ins_c, *ins_t;         // position of the diagonal term in the row's sorted order (nullptr: first / last)
-    double *q_c, *q_t;                // [n][3]; diag_mode: [n] row sums of the weights
+    SellSide cam, time;
     double *sc, *tab;
     unsigned* ticket;
-    int nblk_cam;
-    int add_diag_c;                   // this rank owns the camera diagonal
+    int warps_cam;                    // warps [0, warps_cam) stream camera slices, the rest time slices
     int multi;                        // q_c is a partial sum over ranks: p_c . q_c is taken after the collective
-    int diag_mode;                    // 1: q = row sums of w (weighted degrees), no gather
 };
+
+constexpr int CG_MV_THREADS = 128;
+constexpr int CG_MV_WARPS = CG_MV_THREADS / 32;
+constexpr int CG_U = 8;               // chunks (of 32 slots) per pipeline step of a warp
 
 __device__ __forceinline__ int ld_stream_i(const int* p) {
     int v;
@@ -432,143 +439,152 @@ __device__ __forceinline__ double ld_stream_d(const double* p) {
     return v;
 }
 
-// one chain step: diagonal term at its sorted position, then  acc -= w p  (acc += w in diag mode)
-#define CG_CHAIN_STEP(val)                                                         \
-    do {                                                                           \
-        if (pending && k == ins) { acc = __dadd_rn(acc, diag); pending = false; }  \
-        acc = a.diag_mode ? __dadd_rn(acc, (val)) : __dsub_rn(acc, (val));         \
-        ++k;                                                                       \
-    } while (0)
-
-__global__ void __launch_bounds__(CG_THREADS) cg_matvec_kernel(CgMv a) {
-    if (!a.diag_mode && a.sc[CG_DONE] != 0.0) return;
-    __shared__ __align__(16) double prod[CG_WARPS * CG_TIME_U * 32 * 3];   // camera role: [2][8 chunks][32][3]; time role: [warp][U chunks][32][3]
-    const int tid = threadIdx.x, wv = tid >> 5, lane = tid & 31;
-    const int j = lane >> 2, d = lane & 3;
-    double pq = 0.0;
-    if ((int)blockIdx.x < a.nblk_cam) {
-        // ---- camera role: the whole CTA feeds the 8 x 3 chains of one camera slice
-        for (int64_t slice = blockIdx.x; slice < a.ns_c; slice += a.nblk_cam) {
-            const int c0 = a.sc_ptr[slice], c1 = a.sc_ptr[slice + 1];
-            const int nsteps = (c1 - c0 + CG_WARPS - 1) / CG_WARPS;
-            const int64_t row = SELL_ROWS * slice + j;
-            const bool chain = (wv == 0) && (d < 3) && (row < a.n_c);
-            double acc = 0.0, diag = 0.0, pself = 0.0;
-            int ins = 0x7fffffff, k = 0;
-            bool pending = false;
-            if (chain && !a.diag_mode) {
-                pself = a.p_c[4 * row + d];
-                if (a.add_diag_c) {
-                    diag = __dmul_rn(a.dg_c[row], pself);
-                    pending = true;
-                    ins = a.ins_c ? a.ins_c[row] : 0;
-                }
-            }
-            int idx_n = -1; double w_n = 0.0;
-            if (c0 + wv < c1) { const int64_t slot = 32 * (int64_t)(c0 + wv) + lane; idx_n = ld_stream_i(a.sc_idx + slot); w_n = ld_stream_d(a.sc_w + slot); }
-            for (int s = 0; s <= nsteps; ++s) {
-                const int idx_s = idx_n; const double w_s = w_n;
-                double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-                if (s < nsteps) {
-                    if (a.diag_mode) { g0 = g1 = g2 = 1.0; }
-                    else if (idx_s >= 0) ld_row256(a.p_t + 4 * (int64_t)idx_s, g0, g1, g2);
-                    idx_n = -1; w_n = 0.0;
-                    const int chunk = c0 + CG_WARPS * (s + 1) + wv;
-                    if (chunk < c1) { const int64_t slot = 32 * (int64_t)chunk + lane; idx_n = ld_stream_i(a.sc_idx + slot); w_n = ld_stream_d(a.sc_w + slot); }
-                }
-                if (s > 0 && chain) {
-                    const double* pb = prod + ((s - 1) & 1) * (CG_WARPS * 32 * 3);
+// A warp streams the contiguous chunk range of its slices [s0, s1) through a three-stage software pipeline
+//   A: (index, weight) of step s+2, coalesced        B: 256-bit row gathers of step s+1
+//   C: products of step s -> shared memory, then lanes (j, d < 3) advance the 8 x 3 sequential chains
+// so the only serial work left per element is the chain's own DADD.  Slice boundaries inside a step are
+// handled in the chain loop (rows finish, the next slice's rows start).
+template <bool DIAGMODE>
+__device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, int64_t s1, double* pw, bool count_pq, double& pq) {
+    if (s0 >= s1) return;
+    const int lane = threadIdx.x & 31, j = lane >> 2, d = lane & 3;
+    const int cbeg = __ldg(S.ptr + s0), cend = __ldg(S.ptr + s1);
+    int idx_nx[CG_U]; double w_nx[CG_U];
+    double g[CG_U][3], w_cur[CG_U];
+    auto loadA = [&](int q0) {
 #pragma unroll
-                    for (int u = 0; u < CG_WARPS; ++u)
-#pragma unroll
-                        for (int sub = 0; sub < 4; ++sub) CG_CHAIN_STEP(pb[(u * 32 + 4 * j + sub) * 3 + d]);
-                }
-                if (s < nsteps) {
-                    double* pw = prod + (s & 1) * (CG_WARPS * 32 * 3) + (wv * 32 + lane) * 3;
-                    pw[0] = __dmul_rn(w_s, g0); pw[1] = __dmul_rn(w_s, g1); pw[2] = __dmul_rn(w_s, g2);
-                }
-                __syncthreads();
+        for (int u = 0; u < CG_U; ++u) {
+            idx_nx[u] = -1; w_nx[u] = 0.0;
+            if (q0 + u < cend) {
+                const int64_t slot = 32 * (int64_t)(q0 + u) + lane;
+                idx_nx[u] = ld_stream_i(S.idx + slot); w_nx[u] = ld_stream_d(S.w + slot);
             }
-            if (chain) {
-                if (pending) acc = __dadd_rn(acc, diag);
-                if (a.diag_mode) { if (d == 0) a.q_c[row] = acc; }
-                else {
-                    a.q_c[3 * row + d] = acc;
-                    if (!a.multi) pq += pself * acc;
+        }
+    };
+    auto issueB = [&]() {
+#pragma unroll
+        for (int u = 0; u < CG_U; ++u) {
+            w_cur[u] = w_nx[u];
+            g[u][0] = g[u][1] = g[u][2] = DIAGMODE ? 1.0 : 0.0;
+            if (!DIAGMODE && idx_nx[u] >= 0) ld_row256(S.p_other + 4 * (int64_t)idx_nx[u], g[u][0], g[u][1], g[u][2]);
+        }
+    };
+    // chain state of the current slice (+ the next slice's row constants, fetched one slice ahead)
+    int64_t slice = s0;
+    int slice_end = __ldg(S.ptr + s0 + 1);
+    double acc = 0.0, diag = 0.0, pself = 0.0, n_pself = 0.0, n_dg = 0.0;
+    int ins = 0x7fffffff, n_ins = 0x7fffffff, k = 0;
+    bool pending = false, active = false;
+    auto fetch_row = [&](int64_t sl) {   // constants of slice sl into the n_* registers
+        const int64_t row = SELL_ROWS * sl + j;
+        n_pself = 0.0; n_dg = 0.0; n_ins = S.ins_default;
+        if (!DIAGMODE && sl < s1 && d < 3 && row < S.n_rows) {
+            n_pself = S.p_self[4 * row + d];
+            if (S.add_diag) { n_dg = S.dg[row]; if (S.ins) n_ins = S.ins[row]; }
+        }
+    };
+    auto start_row = [&](int64_t sl) {
+        const int64_t row = SELL_ROWS * sl + j;
+        active = (d < 3) && (row < S.n_rows);
+        acc = 0.0; k = 0; pself = n_pself; pending = false; ins = 0x7fffffff;
+        if (!DIAGMODE && active && S.add_diag) { diag = __dmul_rn(n_dg, pself); pending = true; ins = n_ins; }
+        fetch_row(sl + 1);
+    };
+    auto finish_row = [&](int64_t sl) {
+        if (!active) return;
+        const int64_t row = SELL_ROWS * sl + j;
+        if (pending) acc = __dadd_rn(acc, diag);
+        if (DIAGMODE) { if (d == 0) S.q[row] = acc; }
+        else {
+            S.q[3 * row + d] = acc;
+            if (count_pq) pq += pself * acc;
+        }
+    };
+    fetch_row(s0);
+    start_row(s0);
+    loadA(cbeg);
+    issueB();
+    loadA(cbeg + CG_U);
+    for (int q0 = cbeg; q0 < cend; q0 += CG_U) {
+#pragma unroll
+        for (int u = 0; u < CG_U; ++u) {
+            double* o = pw + (u * 32 + lane) * 3;
+            o[0] = __dmul_rn(w_cur[u], g[u][0]); o[1] = __dmul_rn(w_cur[u], g[u][1]); o[2] = __dmul_rn(w_cur[u], g[u][2]);
+        }
+        issueB();                  // gathers of the next step (their indices arrived one step ago)
+        loadA(q0 + 2 * CG_U);
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < CG_U; ++u) {
+            const int c = q0 + u;
+            if (c < cend) {        // warp-uniform
+                while (c == slice_end) {   // the previous slice's rows are complete (warp-uniform)
+                    finish_row(slice);
+                    ++slice;
+                    slice_end = __ldg(S.ptr + slice + 1);
+                    start_row(slice);
+                }
+                const double* pb = pw + (u * 32 + 4 * j) * 3 + d;
+                if (pending && ins < k + 4) {
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) {
+                        if (pending && k == ins) { acc = __dadd_rn(acc, diag); pending = false; }
+                        acc = DIAGMODE ? __dadd_rn(acc, pb[3 * sub]) : __dsub_rn(acc, pb[3 * sub]);
+                        ++k;
+                    }
+                } else {
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) acc = DIAGMODE ? __dadd_rn(acc, pb[3 * sub]) : __dsub_rn(acc, pb[3 * sub]);
+                    k += 4;
                 }
             }
         }
-    } else {
-        // ---- time role: one warp per slice, CG_TIME_U chunks per step
-        double* pw = prod + wv * (CG_TIME_U * 32 * 3);
-        const int64_t gw = (int64_t)(blockIdx.x - a.nblk_cam) * CG_WARPS + wv;
-        const int64_t nw = (int64_t)(gridDim.x - a.nblk_cam) * CG_WARPS;
-        for (int64_t slice = gw; slice < a.ns_t; slice += nw) {
-            const int c0 = a.st_ptr[slice], c1 = a.st_ptr[slice + 1];
-            const int64_t row = SELL_ROWS * slice + j;
-            const bool chain = (d < 3) && (row < a.n_t);
-            double acc = 0.0, diag = 0.0, pself = 0.0;
-            int ins = 0x7fffffff, k = 0;
-            bool pending = false;
-            if (chain && !a.diag_mode) {
-                pself = a.p_t[4 * row + d];
-                diag = __dmul_rn(a.dg_t[row], pself);
-                pending = true;
-                ins = a.ins_t ? a.ins_t[row] : 0x7fffffff;
-            }
-            for (int q = c0; q < c1; q += CG_TIME_U) {
-                int idx[CG_TIME_U]; double w[CG_TIME_U];
-#pragma unroll
-                for (int u = 0; u < CG_TIME_U; ++u) {
-                    idx[u] = -1; w[u] = 0.0;
-                    if (q + u < c1) { const int64_t slot = 32 * (int64_t)(q + u) + lane; idx[u] = ld_stream_i(a.st_idx + slot); w[u] = ld_stream_d(a.st_w + slot); }
-                }
-                double g[CG_TIME_U][3];
-#pragma unroll
-                for (int u = 0; u < CG_TIME_U; ++u) {
-                    g[u][0] = g[u][1] = g[u][2] = a.diag_mode ? 1.0 : 0.0;
-                    if (!a.diag_mode && idx[u] >= 0) ld_row256(a.p_c + 4 * (int64_t)idx[u], g[u][0], g[u][1], g[u][2]);
-                }
-#pragma unroll
-                for (int u = 0; u < CG_TIME_U; ++u) {
-                    double* o = pw + (u * 32 + lane) * 3;
-                    o[0] = __dmul_rn(w[u], g[u][0]); o[1] = __dmul_rn(w[u], g[u][1]); o[2] = __dmul_rn(w[u], g[u][2]);
-                }
-                __syncwarp();
-                if (chain) {
-#pragma unroll
-                    for (int u = 0; u < CG_TIME_U; ++u)
-                        if (q + u < c1) {
-#pragma unroll
-                            for (int sub = 0; sub < 4; ++sub) CG_CHAIN_STEP(pw[(u * 32 + 4 * j + sub) * 3 + d]);
-                        }
-                }
-                __syncwarp();
-            }
-            if (chain) {
-                if (pending) acc = __dadd_rn(acc, diag);
-                if (a.diag_mode) { if (d == 0) a.q_t[row] = acc; }
-                else {
-                    a.q_t[3 * row + d] = acc;
-                    pq += pself * acc;
-                }
-            }
-        }
+        __syncwarp();
     }
-    if (a.diag_mode) return;
+    // the last slice with chunks, and any trailing slices without (rows with no local edges)
+    for (;;) {
+        finish_row(slice);
+        if (++slice >= s1) break;
+        start_row(slice);
+    }
+}
+
+// q = (J^T J) p in scipy's CSR row order, or (DIAGMODE) the weighted degrees by the same sequential sums
+template <bool DIAGMODE>
+__global__ void __launch_bounds__(CG_MV_THREADS, 4) cg_matvec_kernel(CgMv a) {
+    if (!DIAGMODE && a.sc[CG_DONE] != 0.0) return;
+    __shared__ __align__(16) double prod[CG_MV_WARPS * CG_U * 32 * 3];
+    const int wv = threadIdx.x >> 5;
+    double* pw = prod + wv * (CG_U * 32 * 3);
+    const int64_t gw = (int64_t)blockIdx.x * CG_MV_WARPS + wv;
+    const int64_t nw = (int64_t)gridDim.x * CG_MV_WARPS;
+    double pq = 0.0;
+    if (gw < a.warps_cam) {
+        const int64_t per = (a.cam.n_slices + a.warps_cam - 1) / a.warps_cam;
+        const int64_t s0 = gw * per, s1 = (s0 + per < a.cam.n_slices) ? s0 + per : a.cam.n_slices;
+        cg_stream_rows<DIAGMODE>(a.cam, s0, s1, pw, !a.multi, pq);
+    } else {
+        const int64_t wt = nw - a.warps_cam, me = gw - a.warps_cam;
+        const int64_t per = (a.time.n_slices + wt - 1) / (wt > 0 ? wt : 1);
+        const int64_t s0 = me * per, s1 = (s0 + per < a.time.n_slices) ? s0 + per : a.time.n_slices;
+        cg_stream_rows<DIAGMODE>(a.time, s0, s1, pw, true, pq);
+    }
+    if (DIAGMODE) return;
+    // p . q: camera warps own whole CTAs [0, ceil(warps_cam / 4)) when warps_cam is a multiple of 4 (the host
+    // rounds it), so the two parts can be summed separately and in a fixed order
     const double v[1] = {pq};
-    if (cg_block_partial<1>(v, a.tab, a.ticket)) {
-        const double pq_c = cg_table_sum<1>(a.tab, 0, 0, a.nblk_cam);
-        const double pq_t = cg_table_sum<1>(a.tab, 0, a.nblk_cam, gridDim.x);
+    if (cg_block_partial<1, CG_MV_WARPS>(v, a.tab, a.ticket)) {
+        const int nb_cam = a.warps_cam / CG_MV_WARPS;
+        const double pq_c = cg_table_sum<1, CG_MV_THREADS>(a.tab, 0, 0, nb_cam);
+        const double pq_t = cg_table_sum<1, CG_MV_THREADS>(a.tab, 0, nb_cam, gridDim.x);
         if (threadIdx.x == 0) {
             a.sc[CG_PQ_C] = pq_c; a.sc[CG_PQ_T] = pq_t;
-            if (a.multi) a.q_c[3 * a.n_c] = pq_t;     // rides with the camera accumulator through the collective
+            if (a.multi) a.cam.q[3 * a.cam.n_rows] = pq_t;     // rides with the camera accumulator through the collective
             else a.sc[CG_ALPHA] = a.sc[CG_RHO] / (pq_c + pq_t);
             *a.ticket = 0u;
         }
     }
 }
-#undef CG_CHAIN_STEP
 
 // position of the diagonal entry in a row's ascending-unknown-index order = number of neighbours
 // whose unknown index is smaller than the row's own (warp per slice)
@@ -595,7 +611,7 @@ inline int cg_occupancy_blocks() {
     static int n = 0;
     if (n == 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_matvec_kernel, CG_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_matvec_kernel<false>, CG_MV_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
         n = per_sm * sm_count();
     }
     return n;
@@ -617,35 +633,35 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     const int64_t ns_t = sell_slices(n_t), ns_c = sell_slices(n_c);
 
     CgMv mv;
-    mv.st_ptr = g->st_ptr; mv.st_idx = g->st_idx; mv.st_w = g->st_w; mv.n_t = n_t; mv.ns_t = ns_t;
-    mv.sc_ptr = g->sc_ptr; mv.sc_idx = g->sc_idx; mv.sc_w = g->sc_w; mv.n_c = n_c; mv.ns_c = ns_c;
-    mv.p_c = w.p_c; mv.p_t = w.p_t; mv.dg_c = w.dg_c; mv.dg_t = w.dg_t;
-    mv.ins_c = nullptr; mv.ins_t = nullptr;
-    mv.q_c = w.q_c; mv.q_t = w.q_t; mv.sc = w.sc; mv.tab = w.tab; mv.ticket = w.ticket;
-    mv.add_diag_c = owner; mv.multi = multi; mv.diag_mode = 0;
-    // grid: camera CTAs first (each runs the serial chains of whole slices), then time CTAs; one resident wave
+    mv.cam = SellSide{g->sc_ptr, g->sc_idx, g->sc_w, n_c, ns_c, w.p_t, w.p_c, w.dg_c, nullptr, 0, owner, w.q_c};
+    mv.time = SellSide{g->st_ptr, g->st_idx, g->st_w, n_t, ns_t, w.p_c, w.p_t, w.dg_t, nullptr, 0x7fffffff, 1, w.q_t};
+    mv.sc = w.sc; mv.tab = w.tab; mv.ticket = w.ticket; mv.multi = multi;
+    // One resident wave of 4-warp CTAs.  Camera warps come first, in whole CTAs, one slice each where the
+    // wave allows (a camera slice is one long serial chain per row: its time is its chain, so slices want to
+    // run side by side); the remaining warps split the time slices evenly (contiguous ranges).
     const int cap = cg_occupancy_blocks();
-    static const double cam_frac = getenv("VICAN_B200_CG_CAMFRAC") ? atof(getenv("VICAN_B200_CG_CAMFRAC")) : 0.5;
-    int nblk_cam = (int)(ns_c < (int64_t)(cap * cam_frac) ? ns_c : (int64_t)(cap * cam_frac));
-    if (nblk_cam < 1) nblk_cam = 1;
-    int64_t want_t = (ns_t + CG_WARPS - 1) / CG_WARPS;
-    int nblk_time = (int)(want_t < cap - nblk_cam ? want_t : cap - nblk_cam);
-    if (nblk_time < 1 && ns_t > 0) nblk_time = 1;
-    if (nblk_cam + nblk_time > CG_MAX_BLOCKS) return VB_STATUS_BAD_ARGUMENT;
-    mv.nblk_cam = nblk_cam;
-    const int mv_grid = nblk_cam + nblk_time;
+    static const double cam_frac = getenv("VICAN_B200_CG_CAMFRAC") ? atof(getenv("VICAN_B200_CG_CAMFRAC")) : 0.55;
+    int64_t cam_ctas = (ns_c + CG_MV_WARPS - 1) / CG_MV_WARPS;
+    const int64_t cam_cap = (int64_t)(cap * cam_frac) > 1 ? (int64_t)(cap * cam_frac) : 1;
+    if (cam_ctas > cam_cap) cam_ctas = cam_cap;
+    int64_t time_ctas = (ns_t + CG_MV_WARPS - 1) / CG_MV_WARPS;
+    if (time_ctas > cap - cam_ctas) time_ctas = cap - cam_ctas;
+    if (time_ctas < 1 && ns_t > 0) time_ctas = 1;
+    if (cam_ctas + time_ctas > CG_MAX_BLOCKS) return VB_STATUS_BAD_ARGUMENT;
+    mv.warps_cam = (int)cam_ctas * CG_MV_WARPS;
+    const int mv_grid = (int)(cam_ctas + time_ctas);
 
     if (unk_c != nullptr && unk_t != nullptr) {
         const int capw = sm_count() * 8;
         int gc = (int)((ns_c + CG_WARPS - 1) / CG_WARPS), gt = (int)((ns_t + CG_WARPS - 1) / CG_WARPS);
         cg_ins_kernel<<<gc < capw ? gc : capw, CG_THREADS, 0, st>>>(g->sc_ptr, g->sc_idx, n_c, ns_c, unk_c, unk_t, w.ins_c);
         if (ns_t > 0) cg_ins_kernel<<<gt < capw ? gt : capw, CG_THREADS, 0, st>>>(g->st_ptr, g->st_idx, n_t, ns_t, unk_t, unk_c, w.ins_t);
-        mv.ins_c = w.ins_c; mv.ins_t = w.ins_t;
+        mv.cam.ins = w.ins_c; mv.time.ins = w.ins_t;
     }
     {   // weighted degrees = diagonal of J^T J: the same sequential row sums, over the weights
         CgMv dm = mv;
-        dm.diag_mode = 1; dm.q_c = w.dg_c; dm.q_t = w.dg_t;
-        cg_matvec_kernel<<<mv_grid, CG_THREADS, 0, st>>>(dm);
+        dm.cam.q = w.dg_c; dm.time.q = w.dg_t;
+        cg_matvec_kernel<true><<<mv_grid, CG_MV_THREADS, 0, st>>>(dm);
         VB_KERNEL_CHECK();
         if (allreduce) { int rc = allreduce(actx, w.dg_c, n_c, (void*)st); if (rc) return rc; }
     }
@@ -679,7 +695,7 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     for (int b = 1;; ++b) {
         for (int i = 0; i < batch && enq < maxiter; ++i, ++enq) {
             cg_dir_kernel<<<vgrid, CG_THREADS, 0, st>>>(v);
-            cg_matvec_kernel<<<mv_grid, CG_THREADS, 0, st>>>(mv);
+            cg_matvec_kernel<false><<<mv_grid, CG_MV_THREADS, 0, st>>>(mv);
             if (multi) {
                 int rc = allreduce(actx, w.q_c, 3 * n_c + 8, (void*)st);
                 if (rc) return rc;
