@@ -10,7 +10,7 @@ host = dataclasses.replace(det, **{f: getattr(det, f).cpu().pin_memory() for f i
 def run(src, to_host):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     r = solver.solve_arrays(src.cam, src.time, src.marker, src.R, src.t, src.k_r, src.k_t, I9, q0, 10000, src.n_t, 10,
-                            "conjugate_gradient", to_host=to_host)
+                            "conjugate_gradient", to_host=to_host, reuse_host_buffers=True)
     torch.cuda.synchronize(); return (time.perf_counter() - t0) * 1e3, r.phase_ms
 for i in range(3): print("device", run(det, False))
 for i in range(3): print("host  ", run(host, True))

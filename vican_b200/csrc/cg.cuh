@@ -524,7 +524,7 @@ __device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, in
                     slice_end = __ldg(S.ptr + slice + 1);
                     start_row(slice);
                 }
-                const double* pb = pw + (u * 32 + 4 * j) * 3 + d;
+                const double* pb = pw + (u * 32 + 4 * j) * 3 + (d < 3 ? d : 0);   // lanes d == 3 carry no chain
                 if (pending && ins < k + 4) {
 #pragma unroll
                     for (int sub = 0; sub < 4; ++sub) {
