@@ -111,6 +111,9 @@ typedef struct vb_so3_stats {
 } vb_so3_stats;
 
 const char* vb_version(void);
+/* Number of this library's own kernels launched (and executed) so far in this process: a tally kept by the
+ * host wrappers (CUB's sort / scan kernels and speculative launches that return at once are not counted). */
+int64_t vb_launch_count(void);
 const char* vb_status_string(int code);
 
 /* ---- batched geometry (vican/geometry.py) ------------------------------------------------ */

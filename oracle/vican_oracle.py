@@ -76,10 +76,12 @@ def aggregate_pairs(cam, time, blk, k_r, n_t):
     return cam[first[order]], time[first[order]], B, a
 
 
-def so3sync(pair_cam, pair_time, B, a, n_c, n_t, maxiter, sigma=-1e-6, return_history=False):
+def so3sync(pair_cam, pair_time, B, a, n_c, n_t, maxiter, sigma=-1e-6, return_history=False, timings=None):
     """bipgo.py:243-348 on aggregated edges.  Returns (r_c, r_t) as stored by
     the reference BEFORE the final transpose (bipgo.py:344-348), i.e. the world
-    rotations are r_c[i].T and r_t[j].T."""
+    rotations are r_c[i].T and r_t[j].T.  ``timings`` (a list) receives the wall time of every
+    primal-dual iteration (bench.py's CPU arm)."""
+    import time as _time
     P = _block_matrix(pair_cam, pair_time, B, n_c, n_t)                               # :269
     adj = sp.csr_matrix((a, (pair_cam, pair_time)), shape=(n_c, n_t))                 # :270
     deg_t = np.asarray(adj.sum(axis=0)).ravel()                                       # :271
@@ -95,6 +97,7 @@ def so3sync(pair_cam, pair_time, B, a, n_c, n_t, maxiter, sigma=-1e-6, return_hi
     for _ in range(maxiter):                                                          # :282
         if max_eval <= 1e-6:                                                          # :283
             break
+        _t0 = _time.perf_counter()
         L = (lbd_c - Ppwr)
         L = 0.5 * (L + L.T)                                                           # :285-286
         evals, evecs = np.linalg.eigh(L.toarray())
@@ -114,6 +117,8 @@ def so3sync(pair_cam, pair_time, B, a, n_c, n_t, maxiter, sigma=-1e-6, return_hi
         lt = (U * (1.0 / S)[:, None, :]) @ np.transpose(U, (0, 2, 1))                 # :329
         lbd_t = _block_matrix(bidx_t, bidx_t, lt, n_t, n_t)
         Ppwr = P @ lbd_t @ P.T                                                        # :334
+        if timings is not None:
+            timings.append(_time.perf_counter() - _t0)
     if return_history:
         return r_c, r_t, hist
     return r_c, r_t
@@ -244,13 +249,13 @@ def object_bipartite_se3sync_oracle(src_edges, noise_model_r, noise_model_t, edg
 
 # ------------------------------------------------------------------ array front-end
 def solve_arrays_oracle(cam, time, marker, R, t, k_r, k_t, marker_R, marker_t_inv0, root, n_c, n_t, maxiter,
-                        lsqr_solver):
+                        lsqr_solver, timings=None):
     """Whole path on pre-indexed arrays (used by bench.py's CPU baseline and the large-shape
     tests): bipgo.py:203-348 + :434-487 without the dictionaries.  Unknown order is
     [cameras; time nodes].  Returns (Rw_c, Rw_t, x_c, x_t)."""
     blk = fold_blocks(R, k_r, marker, marker_R, root)
     pc, pt, B, a = aggregate_pairs(cam, time, blk, k_r, n_t)
-    r_c, r_t = so3sync(pc, pt, B, a, n_c, n_t, maxiter)
+    r_c, r_t = so3sync(pc, pt, B, a, n_c, n_t, maxiter, timings=timings)
     Rw_c = np.transpose(r_c, (0, 2, 1))
     Rw_t = np.transpose(r_t, (0, 2, 1))
     J, t_tilde = translation_system(cam, time, marker, t, k_t, marker_R, marker_t_inv0, root, Rw_c, Rw_t, n_c, n_t,

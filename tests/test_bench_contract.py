@@ -9,7 +9,8 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
 def _run(env_extra=None):
-    env = dict(os.environ, TQDM_DISABLE="1", **(env_extra or {}))
+    # the contract is checked on a small sample (the driver's run uses cfg4 at 1/10 scale: ~2 min of CPU work)
+    env = dict(os.environ, TQDM_DISABLE="1", VICAN_B200_REF_SAMPLE="small", **(env_extra or {}))
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                            "--warmup", "0", "--gpus", "1"], capture_output=True, text=True, timeout=600, env=env)
 
@@ -25,6 +26,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["config"]["workload"] == "cfg4" and d["config"]["n_edges"] == 50_000_000
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "sample" in cb and cb["value"] == d["value"]
+    rs = d["config"]["reference_sample"]
+    assert rs["edge_scale_factor"] == 50_000_000 / rs["n_edges"] and cb["sample_iterations"] == rs["maxiter"]
     assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -58,6 +58,7 @@ class VbSo3Stats(C.Structure):
 # name -> (restype, argtypes); must list every symbol declared in include/vican_b200.h
 SIGNATURES = {
     "vb_version": (C.c_char_p, []),
+    "vb_launch_count": (I64, []),
     "vb_status_string": (C.c_char_p, [C.c_int]),
     "vb_se3_compose_batch": (C.c_int, [VP, VP, VP, VP, VP, VP, I64, C.c_int, VP]),
     "vb_se3_invert_batch": (C.c_int, [VP, VP, VP, VP, I64, C.c_int, VP]),

@@ -171,6 +171,7 @@ inline int sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64
     VB_CHECK(cudaMemcpyAsync(&tot_c, sc_ptr + ns_c, sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_KERNEL_CHECK();
     VB_CHECK(cudaStreamSynchronize(st));
+    count_launches(n_t > 0 ? 4 : 2);
     *h_chunks_t = tot_t;
     *h_chunks_c = tot_c;
     return 0;
@@ -190,6 +191,7 @@ inline int sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, 
         sell_fill_cam_kernel<<<grid < cap ? grid : cap, CG_THREADS, 0, st>>>(g->c_segptr, g->n_windows, n_c, g->c_time, g->c_w, ns_c, sc_ptr, sc_idx, sc_w);
     }
     VB_KERNEL_CHECK();
+    count_launches(ns_t > 0 ? 2 : 1);
     return 0;
 }
 
@@ -721,6 +723,9 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
         }
     }
     VB_CHECK(cudaStreamSynchronize(st));   // the speculative tail (no-ops) must not outlive the workspace
+    // executed launches: degrees, init, 3 per executed iteration (+ the scalar kernels of a sharded run);
+    // iterations enqueued after convergence return at their first instruction and are not counted
+    count_launches(2 + (unk_c != nullptr ? 2 : 0) + (multi ? 1 : 0) + (long long)hs[CG_ITERS] * (multi ? 5 : 3));
     if (h_iters) *h_iters = (int32_t)hs[CG_ITERS];
     return status;
 }

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "mat3.cuh"
 
 #define VB_CHECK(expr)                                  \
@@ -20,6 +22,14 @@ constexpr unsigned FULL = 0xffffffffu;
 // 128-byte line so that the three 32-byte row loads of an edge never straddle two L1 lines
 constexpr int GSTRIDE = 16;
 constexpr int NUM_SMS_B200 = 148;
+
+// Tally of this library's own kernel launches (vb:: kernels; CUB's are not counted), bumped by the
+// host wrappers; bench.py reads it through vb_launch_count() around its timed region.
+inline std::atomic<long long>& launch_counter() {
+    static std::atomic<long long> c{0};
+    return c;
+}
+inline void count_launches(long long n) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
 
 inline int sm_count() {
     static int n = 0;

@@ -271,6 +271,7 @@ inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n
     VB_CHECK(cudaMemcpyAsync(&last, w.tmp_b + (n_raw - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CHECK(cudaStreamSynchronize(st));
     *h_n_pairs = last;
+    count_launches(5);   // make_keys, check_sorted, iota (sorted input) or CUB's sort, head_flags, pair_ids
     return 0;
 }
 

@@ -71,6 +71,8 @@ const char* vb_version(void) { return "vican_b200 0.1.0 (sm_100a)"; }
 
 int vb_gather_stride(void) { return GSTRIDE; }
 
+int64_t vb_launch_count(void) { return (int64_t)launch_counter().load(); }
+
 const char* vb_status_string(int code) {
     if (code < 0) return cudaGetErrorString((cudaError_t)(-code));
     switch (code) {
@@ -203,6 +205,7 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     VB_CHECK(cudaStreamSynchronize(st));
     const int64_t n_tiles = (int64_t)last_off;
     *h_n_tiles = n_tiles;
+    count_launches(12);   // pair_start, fold, seg_ptr x2, seg_sum, window keys, window_seg, cam_runs_sum, gather, tile_count, tile_fill
     return 0;
 }
 
@@ -244,7 +247,11 @@ int64_t vb_so3sync_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_so3(
 
 int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, double* r_t, void* workspace,
                    int64_t workspace_bytes, vb_so3_stats* stats, void* stream) {
-    return so3sync_run(g, opt, r_c, r_t, workspace, workspace_bytes, stats, (cudaStream_t)stream);
+    vb_so3_stats local;
+    if (stats == nullptr) stats = &local;
+    const int rc = so3sync_run(g, opt, r_c, r_t, workspace, workspace_bytes, stats, (cudaStream_t)stream);
+    count_launches(stats->kernel_launches);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------- translation
@@ -261,6 +268,7 @@ int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair
     seg_sum3_kernel<<<tr_warp_grid(g->n_t), TR_THREADS, 0, st>>>(g->t_rowptr, nullptr, pair_g, 1.0, rhs_t, g->n_t);
     cam_runs_sum3_kernel<<<tr_warp_grid(g->n_c), TR_THREADS, 0, st>>>(g->c_segptr, g->n_windows, g->n_c, g->c_order, pair_g, -1.0, rhs_c);
     VB_KERNEL_CHECK();
+    count_launches(3);
     return 0;
 }
 
@@ -346,6 +354,7 @@ int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw
     VB_CHECK(cudaStreamSynchronize(st));
     if (h_istop) *h_istop = (int32_t)hs[LS_ISTOP];
     if (h_iters) *h_iters = (int32_t)hs[LS_ITN];
+    count_launches(12 + 12 * (long long)hs[LS_ITN]);   // set-up + 12 kernels per bidiagonalisation step
     return 0;
 }
 
