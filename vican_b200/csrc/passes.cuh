@@ -125,18 +125,20 @@ struct Item {
     bool last, valid;
 };
 
-// item loads: block rows (LDS) + far-endpoint indices (LDS) + 256-bit row gathers, all issued back to back
-__device__ __forceinline__ void item_load(const unsigned char* bufp, const double* __restrict__ G, const Item& it, int e,
-                                          int k, double (&b)[5][3], double (&x)[5][3]) {
+// item loads: block rows (LDS) + far-endpoint indices (LDS) + 256-bit row gathers, all issued back to back.
+// Returns the mask of rounds in which this lane holds a real edge; the FMAs of the other rounds are skipped
+// (no zero-filling of the 30 operand registers per item).
+__device__ __forceinline__ unsigned item_load(const unsigned char* bufp, const double* __restrict__ G, const Item& it, int e,
+                                              int k, bool lane_on, double (&b)[5][3], double (&x)[5][3]) {
     const double* sB = reinterpret_cast<const double*>(bufp);
     const int* sI = reinterpret_cast<const int*>(bufp + BUF_B_BYTES);
     const int offB = it.a - (it.a & ~1), offI = it.a - (it.a & ~3), n_e = it.b - it.a;
+    unsigned vmask = 0u;
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
         const int off = EDGES_PER_ROUND * u + e;
-        b[u][0] = b[u][1] = b[u][2] = 0.0;
-        x[u][0] = x[u][1] = x[u][2] = 0.0;
-        if ((e < EDGES_PER_ROUND) && (off < n_e)) {
+        if (lane_on && (off < n_e)) {
+            vmask |= 1u << u;
             const int node = sI[offI + off];
             // row k of the staged block: row k of B for the time pass, row k of B^T (= column k of B) for the
             // camera pass, whose copy of the blocks is stored transposed
@@ -147,13 +149,13 @@ __device__ __forceinline__ void item_load(const unsigned char* bufp, const doubl
             ld_row256(G + GSTRIDE * (size_t)node + 4 * k, x[u][0], x[u][1], x[u][2]);
         }
     }
+    return vmask;
 }
 
-__device__ __forceinline__ void item_fma(const Item& it, const double (&b)[5][3], const double (&x)[5][3], double (&acc)[9]) {
-    const int n_e = it.b - it.a;
+__device__ __forceinline__ void item_fma(unsigned vmask, const double (&b)[5][3], const double (&x)[5][3], double (&acc)[9]) {
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
-        if (EDGES_PER_ROUND * u < n_e) {   // warp-uniform: skip empty tail rounds
+        if (vmask & (1u << u)) {
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -194,7 +196,22 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     if (warp >= n_seg) return;
 
     const uint64_t pf = policy_evict_first();
-    const int e = lane / 3, k = lane - 3 * e;   // lanes 30, 31: e = 10 -> idle in the loop, zero in the reduction
+    // Lane -> (edge of the round, block row).  Quad q (lanes 4q .. 4q+3) holds the three rows of edge q in its
+    // lanes 0-2: their 256-bit gathers hit ONE 128-byte line (a padded node block), i.e. one L1 wavefront.
+    // The fourth lanes of the quads carry the six rows of edges 8 and 9 (two stay idle), assigned so that the
+    // LDS.64 of the staged block rows stay bank-conflict free.  10 edges per round at 14 gather wavefronts
+    // (a dense lane = 3 e + k packing straddles quads: 15-19 wavefronts per round, measured 0.63 per row).
+    const int quad = lane >> 2, qr = lane & 3;
+    int e, k;
+    bool lane_on = true;
+    if (qr < 3) { e = quad; k = qr; }
+    else {
+        // quad:      0      1      2     3     4      5      6      7
+        // carries: (9,1)  (9,2)   idle  idle  (8,0)  (8,1)  (8,2)  (9,0)
+        e = (int)((0x98880099u >> (4 * quad)) & 0xFu);
+        k = (int)((0x02100021u >> (4 * quad)) & 0xFu);
+        lane_on = (quad != 2) && (quad != 3);
+    }
 
     // ---- item iterator (warp-uniform).  Row pointers are fetched two segments ahead of their use.
     int it_seg = warp, it_s = __ldg(seg_ptr + warp), it_e = __ldg(seg_ptr + warp + 1), it_pos = it_s;
@@ -238,10 +255,12 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     };
 
     double bq[5][3], xq[5][3];
+    unsigned vmask = 0u;
     double lamC[3] = {0.0, 0.0, 0.0}, lamN[3] = {0.0, 0.0, 0.0};
     auto load = [&](const Item& it, int buf, double (&lam)[3]) {
+        vmask = 0u;
         if (!it.valid) return;
-        item_load(wbuf + buf * BUF_BYTES, G, it, e, k, bq, xq);
+        vmask = item_load(wbuf + buf * BUF_BYTES, G, it, e, k, lane_on, bq, xq);
         if (MODE == 0 && it.last && lane < 9) {   // Lambda_T row for this segment's epilogue
             if (lamT != nullptr) {
                 const double* L = lamT + 9 * (size_t)it.seg + 3 * (lane / 3);
@@ -262,7 +281,7 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     load(i0, 0, lamC);
     int buf0 = 0;
     while (i0.valid) {
-        item_fma(i0, bq, xq, acc);          // registers of item k are free after this
+        item_fma(vmask, bq, xq, acc);       // registers of item k are free after this
         i2 = next_item();
         issue(i2, buf0);                     // item k's stage is free (all its LDS fed the FMAs above)
         wait_buf(i1, buf0 ^ 1);
