@@ -80,7 +80,11 @@ typedef struct vb_so3_options {
     int32_t no_shortcut;    /* != 0: always run the primal multiply as two edge passes (see stats->shortcut_outer) */
     int32_t identity_start; /* != 0: first eigen-solve starts from identity blocks instead of the one-hop spanning
                              * estimate project_SO3((P Lambda_T P^T E_0)_c) (2 extra edge passes, ~half the steps) */
-    int32_t reserved;
+    int32_t eval_gap;       /* != 0: also compute the next three eigenvalues (lambda_4..6) in every outer iteration, by a
+                             * second eigen-solve on the operator deflated by the converged eigenvectors -- the
+                             * reference's diagnostics (evals, eigengap = |lambda_4 / lambda_3|, bipgo.py:291, :336-339)
+                             * and its early exit `max |lambda_1..5| <= 1e-6` (bipgo.py:283, :292), which can only
+                             * fire on (nearly) disconnected graphs.  Costs one more eigen-solve per iteration. */
     void*   peer_ctx;       /* vb_peer_create context: the camera pass runs FUSED with its cross-rank sum over
                              * NVLink peer memory (allreduce / allreduce_ctx are then used for the few other
                              * reductions only and may point at vb_peer_allreduce); NULL: separate collective */
@@ -107,7 +111,9 @@ typedef struct vb_so3_stats {
      * its start block R (the previous r_c) at the first step, project_SO3(V_c V_0^-1) = R_c R_0^T exactly and
      * P Lambda_T P^T r_c = Y R_0^T with Y already computed for the eigen-residual (bipgo.py:295-300) */
     int32_t shortcut_outer;
-    int32_t reserved2;
+    int32_t early_exit;     /* 1: the loop stopped before maxiter because max |lambda_1..5| <= 1e-6 (eval_gap only) */
+    /* eval_gap: the five eigenvalues nearest zero of every outer iteration (bipgo.py:288-292), first 64 iterations */
+    double  evals_hist[64][5];
 } vb_so3_stats;
 
 const char* vb_version(void);

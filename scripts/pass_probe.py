@@ -26,3 +26,4 @@ for name, fn, kind in (("time", lambda: lib.vb_pass_time(C.byref(g.cgraph), 0, p
     ms = a.elapsed_time(b) / 20
     nb = g.pass_bytes(kind)
     print("%s pass: %.4f ms  %.0f GB/s  frac of 6461: %.3f" % (name, ms, nb / ms * 1e-6, nb / ms * 1e-6 / 6461.2))
+print("checksum Wt %.15e  Y %.15e  var %s" % (float(Wt.double().abs().sum()), float(Y.abs().sum()), os.environ.get("VICAN_B200_PASS_VAR", "default")))

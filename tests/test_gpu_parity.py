@@ -395,3 +395,56 @@ def test_float32_call_of_the_notebook(cuda):
     R64 = np.stack([ref64[k][0] for k in keys])
     assert geodesic_rad(Ra, R64).max() <= 1.2e-7
     assert rel_translation_err(ta, np.stack([ref64[k][1] for k in keys])).max() <= TRANS_REL_TOL
+
+
+def test_verbose_reports_the_references_eigenvalue_readout(cuda, capsys):
+    """bipgo.py:288-292, :336-339: the five eigenvalues nearest zero of every outer iteration (three ~0 and
+    lambda_4, lambda_5) and eigengap = |lambda_4 / lambda_3|, against the oracle's dense eigen-solve."""
+    from vican_b200 import bipgo
+    g = syn.make_camera_network(5, 15, 120, 4, 5, 2)
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(True)
+    out = bipgo.bipartite_se3sync(edges, constraints, nr, nt, ef, 5, "conjugate_gradient", dtype=np.float64, verbose=True)
+    printed = capsys.readouterr().out
+    assert printed.count("eigengap=") == 5 and "evals0=" in printed
+    ref, info = orc.bipartite_se3sync_oracle(edges, constraints, nr, nt, ef, 5, "conjugate_gradient", return_info=True)
+    rot, tr = compare(out, ref)
+    assert rot <= 1e-8 and tr <= TRANS_REL_TOL            # the diagnostics do not disturb the solve
+    ev = np.asarray(bipgo.last_info["evals"])
+    assert ev.shape == (5, 5) and bipgo.last_info["n_components"] == 1 and not bipgo.last_info["early_exit"]
+    for it in range(5):
+        o = np.sort(np.abs(info["evals"][it]))            # oracle: 5 nearest sigma (3 tiny, then lambda_4, lambda_5)
+        d = np.sort(np.abs(ev[it]))
+        scale = o[4]
+        assert np.all(np.abs(d[:3] - o[:3]) <= 1e-9 * scale), (it, d, o)
+        assert np.all(np.abs(d[3:] - o[3:]) <= 1e-6 * scale), (it, d, o)
+
+
+def test_early_exit_on_a_disconnected_graph_like_the_reference(cuda):
+    """bipgo.py:283-284: the loop stops once max |lambda_1..5| <= 1e-6, which needs lambda_4, lambda_5 ~ 0, i.e. a
+    graph with more than one component (six zero modes).  Same stopping iteration as the oracle."""
+    import warnings
+    from vican_b200 import bipgo
+    a = syn.make_camera_network(1, 6, 40, 3, 4, 2, sigma_R=0.0, sigma_t=0.0)
+    b = syn.make_camera_network(2, 6, 40, 3, 4, 2, sigma_R=0.0, sigma_t=0.0)
+    ea, cons = syn.to_edge_dict(a, SE3)
+    eb, _ = syn.to_edge_dict(b, SE3)
+    edges = dict(ea)
+    for (c, tm), v in eb.items():                           # second component: cameras 6..11, timesteps 40..79
+        t, m = tm.split("_")
+        edges[(str(int(c) + 6), "%d_%s" % (int(t) + 40, m))] = v
+    nr, nt, ef = callables(True)
+    maxiter = 12
+    ref, info = orc.bipartite_se3sync_oracle(edges, cons, nr, nt, ef, maxiter, "conjugate_gradient", return_info=True)
+    n_ref = len(info["evals"])
+    assert n_ref < maxiter                                  # the reference's early exit fired
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        out = bipgo.bipartite_se3sync(edges, cons, nr, nt, ef, maxiter, "conjugate_gradient", dtype=np.float64)
+    assert any("connected components" in str(w.message) for w in wlist)
+    li = bipgo.last_info
+    assert li["n_components"] == 2 and li["early_exit"] and li["outer_done"] == n_ref, (li["outer_done"], n_ref, li["evals"])
+    assert all(np.all(np.isfinite(v.R())) and np.all(np.isfinite(v.t())) for v in out.values())
+    # the gauge camera's component is determined: its cameras agree with the oracle
+    for c in range(6):
+        assert geodesic_rad(out[str(c)].R(), ref[str(c)][0]).max() <= ROT_TOL_RAD

@@ -41,7 +41,7 @@ class VbGraph(C.Structure):
 
 class VbSo3Options(C.Structure):
     _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP),
-                ("profile_events", I32), ("no_shortcut", I32), ("identity_start", I32), ("reserved", I32),
+                ("profile_events", I32), ("no_shortcut", I32), ("identity_start", I32), ("eval_gap", I32),
                 ("peer_ctx", VP)]
 
 
@@ -51,7 +51,7 @@ class VbSo3Stats(C.Structure):
         ("kernel_launches", I32), ("stalled_outer", I32),
         ("theta", F64 * 3), ("resid", F64 * 3), ("anorm", F64), ("inner_per_outer", I32 * 64),
         ("time_pass_ms", F64), ("cam_pass_ms", F64), ("time_pass_timed", I32), ("cam_pass_timed", I32),
-        ("shortcut_outer", I32), ("reserved2", I32),
+        ("shortcut_outer", I32), ("early_exit", I32), ("evals_hist", (F64 * 5) * 64),
     ]
 
 

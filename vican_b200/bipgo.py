@@ -149,15 +149,42 @@ class EigenConvergenceWarning(RuntimeWarning):
     tolerance (the reference's ARPACK call raises ArpackNoConvergence in that situation)."""
 
 
+def _n_components(tab: EdgeTable) -> int:
+    """Connected components of the bipartite detection graph (host, scipy csgraph: plumbing)."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    n_c, n_t = tab.n_c, tab.n_t
+    adj = sp.coo_matrix((np.ones(tab.n_raw, dtype=np.int8), (tab.cam_idx, n_c + tab.time_idx.astype(np.int64))),
+                        shape=(n_c + n_t, n_c + n_t))
+    return int(connected_components(adj, directed=False, return_labels=False))
+
+
 def _solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: Optional[str], mode: str = "parity",
-                 tol: float = 1e-13, strict: bool = False):
+                 tol: float = 1e-13, strict: bool = False, verbose: bool = False):
     t0 = _time.perf_counter()
     if tab.n_c < 3:
         raise ValueError("the rotation stage needs at least 3 camera nodes (the reference asks ARPACK for 5 "
                          "eigenpairs of a 3 n_c x 3 n_c matrix); got %d" % tab.n_c)
     g = _solver.DeviceGraph(tab.cam_idx, tab.time_idx, tab.marker_idx, tab.R, tab.k_r, tab.k_t, tab.markerC,
                             tab.n_c, tab.n_t, round_kr_f32=tab.round_kr_f32)
-    rot = _solver.solve_rotations(g, maxiter, tol=tol)
+    # The reference leaves its loop early when the five eigenvalues nearest zero are all <= 1e-6
+    # (bipgo.py:283-292).  lambda_4, lambda_5 are O(degree) on a connected graph, so the test can only fire when
+    # the graph falls apart into components: only then (or for verbose callers, who get the reference's
+    # evals / eigengap read-out) is the second eigen-solve per iteration paid for.
+    n_comp = _n_components(tab)
+    if n_comp > 1:
+        warnings.warn("the detection graph has %d connected components: poses outside the gauge camera's component "
+                      "are undetermined (the reference returns an arbitrary member of a 3 x %d dimensional "
+                      "eigenspace there)" % (n_comp, n_comp), RuntimeWarning, stacklevel=3)
+    rot = _solver.solve_rotations(g, maxiter, tol=tol, eval_gap=bool(verbose or n_comp > 1))
+    if verbose:
+        for it in range(min(rot.stats.outer_done, 64)):
+            ev = list(rot.stats.evals_hist[it])
+            gap = abs(ev[3] / ev[2]) if ev[2] != 0.0 else float("inf")       # bipgo.py:291
+            print("Optimizing %d/%d: evals0=%1.3e, evals1=%1.3e, evals2=%1.3e, eigengap=%1.3e"
+                  % (it + 1, maxiter, ev[0], ev[1], ev[2], gap))
+        if rot.stats.early_exit:
+            print("stopped after %d of %d iterations: max |eval| <= 1e-6" % (rot.stats.outer_done, maxiter))
     if rot.status == 2 or rot.stats.stalled_outer > 0:
         msg = ("eigen-iteration stopped at its step cap in %d of %d outer iterations (residual %.2e, scale %.2e): "
                "the poses may be inaccurate (outliers / weak connectivity?)"
@@ -176,16 +203,19 @@ def _solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: Optional[str], mode:
         inner_per_outer=list(rot.stats.inner_per_outer[:min(maxiter, 64)]),
         time_passes=rot.stats.time_passes, cam_passes=rot.stats.cam_passes,
         theta=list(rot.stats.theta), resid=list(rot.stats.resid), eig_status=rot.status,
+        outer_done=rot.stats.outer_done, early_exit=bool(rot.stats.early_exit), n_components=n_comp,
+        evals=[list(rot.stats.evals_hist[i]) for i in range(min(rot.stats.outer_done, 64))] if (verbose or n_comp > 1) else None,
         trans_iters=None if tr is None else tr.iters, trans_istop=None if tr is None else tr.istop,
         device_seconds=_time.perf_counter() - t0))
     return g, rot, tr
 
 
 def large_bipartite_so3sync(src_edges: dict, constraints: dict, noise_model: Callable, edge_filter: Callable,
-                            maxiter: int, dtype=np.float32) -> dict:
-    """Rotation stage only (vican/bipgo.py:145-350): {camera id: R, f"{t}_0": R} wrt the world."""
+                            maxiter: int, dtype=np.float32, *, verbose: bool = False) -> dict:
+    """Rotation stage only (vican/bipgo.py:145-350): {camera id: R, f"{t}_0": R} wrt the world.
+    ``verbose`` prints the reference's per-iteration read-out (evals0..2, eigengap; bipgo.py:336-339)."""
     tab = EdgeTable(src_edges, constraints, noise_model, lambda e: 1.0, edge_filter)
-    _, rot, _ = _solve_table(tab, maxiter, None)
+    _, rot, _ = _solve_table(tab, maxiter, None, verbose=verbose)
     Rc, Rt = rot.world_rotations()
     Rc, Rt = Rc.cpu().numpy().astype(dtype), Rt.cpu().numpy().astype(dtype)
     out = {}
@@ -198,7 +228,7 @@ def large_bipartite_so3sync(src_edges: dict, constraints: dict, noise_model: Cal
 
 def bipartite_se3sync(src_edges: dict, constraints: dict, noise_model_r: Callable, noise_model_t: Callable,
                       edge_filter: Callable, maxiter: int, lsqr_solver: str, dtype=np.float32,
-                      *, mode: str = "parity", strict: bool = False) -> dict:
+                      *, mode: str = "parity", strict: bool = False, verbose: bool = False) -> dict:
     """SE(3) synchronisation in a bipartite camera / object-timestep graph with node
     constraints; same contract as ``vican/bipgo.py:353-490``.  Returns a dict with every camera
     id and every ``f"{t}_0"`` node mapped to an ``SE3`` pose wrt the world.
@@ -208,20 +238,23 @@ def bipartite_se3sync(src_edges: dict, constraints: dict, noise_model_r: Callabl
     Raises ``ValueError`` for an unknown ``lsqr_solver`` (the reference falls through to a
     NameError) and ``ConvergenceError`` (an ``AssertionError``) if CG does not converge.  An
     eigen-iteration that stops at its step cap emits ``EigenConvergenceWarning`` (``strict=True``:
-    raises ``ConvergenceError``, like ARPACK's ``ArpackNoConvergence`` in the reference)."""
+    raises ``ConvergenceError``, like ARPACK's ``ArpackNoConvergence`` in the reference).
+    ``verbose=True`` prints what the reference's progress bar shows (evals0..2, eigengap per iteration,
+    bipgo.py:336-339).  The reference's early exit ``max |lambda_1..5| <= 1e-6`` (bipgo.py:283) is applied
+    whenever it can fire, i.e. when the detection graph is not connected (checked on the host)."""
     if lsqr_solver not in ("conjugate_gradient", "direct"):
         raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
     tab = EdgeTable(src_edges, constraints, noise_model_r, noise_model_t, edge_filter)
-    return solve_table(tab, maxiter, lsqr_solver, dtype=dtype, mode=mode, strict=strict)
+    return solve_table(tab, maxiter, lsqr_solver, dtype=dtype, mode=mode, strict=strict, verbose=verbose)
 
 
 def solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: str, dtype=np.float32, *, mode: str = "parity",
-                strict: bool = False) -> dict:
+                strict: bool = False, verbose: bool = False) -> dict:
     """``bipartite_se3sync`` from an already flattened ``EdgeTable`` (``EdgeTable.from_arrays``,
     ``io.EdgeAccumulator.table``): same result dictionary, no dictionary walk, no callables."""
     if lsqr_solver not in ("conjugate_gradient", "direct"):
         raise ValueError("lsqr_solver must be 'conjugate_gradient' or 'direct', got %r" % (lsqr_solver,))
-    _, rot, tr = _solve_table(tab, maxiter, lsqr_solver, mode=mode, strict=strict)
+    _, rot, tr = _solve_table(tab, maxiter, lsqr_solver, mode=mode, strict=strict, verbose=verbose)
     Rc, Rt = rot.world_rotations()
     Rc, Rt = Rc.cpu().numpy().astype(dtype), Rt.cpu().numpy().astype(dtype)
     xc, xt = tr.x_c.cpu().numpy(), tr.x_t.cpu().numpy()
@@ -240,7 +273,7 @@ def solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: str, dtype=np.float32
 
 def object_bipartite_se3sync(src_edges: dict, noise_model_r: Callable, noise_model_t: Callable,
                              edge_filter: Callable, maxiter: int, lsqr_solver: str, dtype=np.float32,
-                             *, mode: str = "parity", strict: bool = False) -> dict:
+                             *, mode: str = "parity", strict: bool = False, verbose: bool = False) -> dict:
     """Object calibration (single object, moving camera); same contract as
     ``vican/bipgo.py:493-545``: markers take the camera role, timesteps the object role, every
     pose is inverted (through float32, as ``SE3.inv`` does) and only marker poses are returned."""
@@ -272,5 +305,5 @@ def object_bipartite_se3sync(src_edges: dict, noise_model_r: Callable, noise_mod
                                             "im_filename": v["im_filename"]}
     out = bipartite_se3sync(edges, constraints={root: SE3(pose=np.eye(4))}, noise_model_r=noise_model_r,
                             noise_model_t=noise_model_t, edge_filter=edge_filter, maxiter=maxiter,
-                            lsqr_solver=lsqr_solver, dtype=dtype, mode=mode, strict=strict)
+                            lsqr_solver=lsqr_solver, dtype=dtype, mode=mode, strict=strict, verbose=verbose)
     return {k: v for k, v in out.items() if "_" not in k}                    # bipgo.py:543

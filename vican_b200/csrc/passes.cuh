@@ -52,6 +52,7 @@ constexpr int WARP_SCRATCH = 128;                                     // 9 doubl
 constexpr int WARP_SMEM = 2 * BUF_BYTES + WARP_SCRATCH;
 constexpr int PASS_SMEM = PASS_WARPS * WARP_SMEM + PASS_WARPS * 2 * 8;
 constexpr int EDGES_PER_ROUND = 10;
+constexpr int PASS_VAR_DEFAULT = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -126,19 +127,18 @@ struct Item {
 };
 
 // item loads: block rows (LDS) + far-endpoint indices (LDS) + 256-bit row gathers, all issued back to back.
-// Returns the mask of rounds in which this lane holds a real edge; the FMAs of the other rounds are skipped
-// (no zero-filling of the 30 operand registers per item).
-__device__ __forceinline__ unsigned item_load(const unsigned char* bufp, const double* __restrict__ G, const Item& it, int e,
-                                              int k, bool lane_on, double (&b)[5][3], double (&x)[5][3]) {
+// Lanes without an edge in a round get a ZERO block row (their gathered row keeps whatever finite value the
+// registers held: x is cleared once before the loop), so the FMAs of a round need only a warp-uniform guard.
+__device__ __forceinline__ void item_load(const unsigned char* bufp, const double* __restrict__ G, const Item& it, int e,
+                                          int k, bool lane_on, double (&b)[5][3], double (&x)[5][3]) {
     const double* sB = reinterpret_cast<const double*>(bufp);
     const int* sI = reinterpret_cast<const int*>(bufp + BUF_B_BYTES);
     const int offB = it.a - (it.a & ~1), offI = it.a - (it.a & ~3), n_e = it.b - it.a;
-    unsigned vmask = 0u;
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
         const int off = EDGES_PER_ROUND * u + e;
+        b[u][0] = b[u][1] = b[u][2] = 0.0;
         if (lane_on && (off < n_e)) {
-            vmask |= 1u << u;
             const int node = sI[offI + off];
             // row k of the staged block: row k of B for the time pass, row k of B^T (= column k of B) for the
             // camera pass, whose copy of the blocks is stored transposed
@@ -149,13 +149,13 @@ __device__ __forceinline__ unsigned item_load(const unsigned char* bufp, const d
             ld_row256(G + GSTRIDE * (size_t)node + 4 * k, x[u][0], x[u][1], x[u][2]);
         }
     }
-    return vmask;
 }
 
-__device__ __forceinline__ void item_fma(unsigned vmask, const double (&b)[5][3], const double (&x)[5][3], double (&acc)[9]) {
+__device__ __forceinline__ void item_fma(const Item& it, const double (&b)[5][3], const double (&x)[5][3], double (&acc)[9]) {
+    const int n_e = it.b - it.a;
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
-        if (vmask & (1u << u)) {
+        if (EDGES_PER_ROUND * u < n_e) {   // warp-uniform: skip empty tail rounds
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -174,7 +174,9 @@ __device__ __forceinline__ void item_fma(unsigned vmask, const double (&b)[5][3]
 //   FMA(item k)  ->  TMA issue(item k+2)  ->  wait + loads(item k+1)  ->  epilogue(segment of k, if it ends)
 // so the segment reduction / store overlaps the gather round trip of the next item and the TMA copy
 // of an item has one full iteration to land.
-template <int MODE>
+// VAR (tuning variants, selected per launch): bit 0 = quad-aligned lane mapping (else dense lane = 3 e + k),
+// bit 1 = MODE 0 epilogue through shuffles (else through the per-warp scratch in shared memory).
+template <int MODE, int VAR>
 __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node,
                                                const int* __restrict__ idx, const double* __restrict__ B,
                                                const double* __restrict__ G, const double* __restrict__ lamT,
@@ -204,7 +206,8 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     const int quad = lane >> 2, qr = lane & 3;
     int e, k;
     bool lane_on = true;
-    if (qr < 3) { e = quad; k = qr; }
+    if (!(VAR & 1)) { e = lane / 3; k = lane - 3 * e; lane_on = lane < 30; }
+    else if (qr < 3) { e = quad; k = qr; }
     else {
         // quad:      0      1      2     3     4      5      6      7
         // carries: (9,1)  (9,2)   idle  idle  (8,0)  (8,1)  (8,2)  (9,0)
@@ -255,12 +258,12 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     };
 
     double bq[5][3], xq[5][3];
-    unsigned vmask = 0u;
+#pragma unroll
+    for (int u = 0; u < 5; ++u) xq[u][0] = xq[u][1] = xq[u][2] = 0.0;
     double lamC[3] = {0.0, 0.0, 0.0}, lamN[3] = {0.0, 0.0, 0.0};
     auto load = [&](const Item& it, int buf, double (&lam)[3]) {
-        vmask = 0u;
         if (!it.valid) return;
-        vmask = item_load(wbuf + buf * BUF_BYTES, G, it, e, k, lane_on, bq, xq);
+        item_load(wbuf + buf * BUF_BYTES, G, it, e, k, lane_on, bq, xq);
         if (MODE == 0 && it.last && lane < 9) {   // Lambda_T row for this segment's epilogue
             if (lamT != nullptr) {
                 const double* L = lamT + 9 * (size_t)it.seg + 3 * (lane / 3);
@@ -281,7 +284,7 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     load(i0, 0, lamC);
     int buf0 = 0;
     while (i0.valid) {
-        item_fma(vmask, bq, xq, acc);       // registers of item k are free after this
+        item_fma(i0, bq, xq, acc);          // registers of item k are free after this
         i2 = next_item();
         issue(i2, buf0);                     // item k's stage is free (all its LDS fed the FMAs above)
         wait_buf(i1, buf0 ^ 1);
@@ -290,7 +293,16 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
             int vidx;
             const double tot = reduce_scatter9(acc, lane, &vidx);
             const bool holder = ((lane & 1) == 0) && (vidx < 9);
-            if (MODE == 0) {
+            if (MODE == 0 && (VAR & 2)) {
+                // total m sits in the lane pair inv[m] (see reduce_scatter9): output lane (a, j) fetches column j
+                const int a = lane / 3, j = lane - 3 * a;
+                const unsigned long long inv = 0xCA9854210ULL;   // m -> pair index
+                const int jj = lane < 9 ? j : 0;
+                const double z0 = shfl(tot, 2 * (int)((inv >> (4 * jj)) & 0xF));
+                const double z1 = shfl(tot, 2 * (int)((inv >> (4 * (3 + jj))) & 0xF));
+                const double z2 = shfl(tot, 2 * (int)((inv >> (4 * (6 + jj))) & 0xF));
+                if (lane < 9) out[GSTRIDE * (size_t)i0.seg + 4 * a + j] = lamC[0] * z0 + lamC[1] * z1 + lamC[2] * z2;
+            } else if (MODE == 0) {
                 if (holder) scratch[vidx] = tot;
                 __syncwarp();
                 if (lane < 9) {
@@ -313,7 +325,7 @@ __device__ __forceinline__ void edge_pass_body(const int* __restrict__ seg_ptr, 
     }
 }
 
-template <int MODE, int CTAS>
+template <int MODE, int CTAS, int VAR>
 __global__ void __launch_bounds__(PASS_THREADS, CTAS)
 edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_node, const int* __restrict__ idx,
                  const double* __restrict__ B, const double* __restrict__ G, const double* __restrict__ lamT,
@@ -321,7 +333,7 @@ edge_pass_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ seg_no
     // speculatively enqueued launches (the host polls the eigen-solver's convergence flag one
     // iteration late) turn into no-ops once the flag is set
     if (skip_flag != nullptr && *skip_flag != 0.0) return;
-    edge_pass_body<MODE>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg);
+    edge_pass_body<MODE, VAR>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg);
 }
 
 // Camera pass FUSED with the cross-rank sum of its result (edge-sharded multi-GPU runs): the
@@ -337,7 +349,7 @@ edge_pass_fused_kernel(const int* __restrict__ seg_ptr, const int* __restrict__ 
     if (skip_flag != nullptr && *skip_flag != 0.0) return;   // identical on every rank (replicated, bitwise equal state)
     const unsigned long long epoch = pd.ctrl[pd.rank]->epoch + 1ull;
     double* mine = pd.buf[pd.rank] + (long long)(epoch & 1ull) * pd.cap;
-    edge_pass_body<2>(seg_ptr, seg_node, idx, B, G, nullptr, mine, n_seg);
+    edge_pass_body<2, PASS_VAR_DEFAULT>(seg_ptr, seg_node, idx, B, G, nullptr, mine, n_seg);
     peer_publish(pd, epoch);
     peer_reduce(pd, epoch, Y, n_y);
 }
@@ -382,18 +394,31 @@ inline int pass_grid(int64_t n_segments, int ctas_per_sm) {
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-template <int MODE>
-inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
-                            const double* lamT, double* out, int64_t n_seg, cudaStream_t st, const double* skip_flag) {
+template <int MODE, int VAR>
+inline int launch_edge_pass_var(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
+                                const double* lamT, double* out, int64_t n_seg, cudaStream_t st, const double* skip_flag) {
     constexpr int CTAS = PASS_CTAS_PER_SM;   // 5 or 6 CTAs / SM (80-96 registers) measured slower, see profiles/
     static bool attr_set = false;
     if (!attr_set) {
-        VB_CHECK(cudaFuncSetAttribute(edge_pass_kernel<MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
+        VB_CHECK(cudaFuncSetAttribute(edge_pass_kernel<MODE, CTAS, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
         attr_set = true;
     }
-    edge_pass_kernel<MODE, CTAS><<<pass_grid(n_seg, CTAS), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg, skip_flag);
+    edge_pass_kernel<MODE, CTAS, VAR><<<pass_grid(n_seg, CTAS), PASS_THREADS, PASS_SMEM, st>>>(seg_ptr, seg_node, idx, B, G, lamT, out, (int)n_seg, skip_flag);
     VB_KERNEL_CHECK();
     return 0;
+}
+
+template <int MODE>
+inline int launch_edge_pass(const int* seg_ptr, const int* seg_node, const int* idx, const double* B, const double* G,
+                            const double* lamT, double* out, int64_t n_seg, cudaStream_t st, const double* skip_flag) {
+    // VICAN_B200_PASS_VAR: tuning variants of the kernel (profiles/r2_edge_pass.md); default = PASS_VAR_DEFAULT
+    static const int var = getenv("VICAN_B200_PASS_VAR") ? atoi(getenv("VICAN_B200_PASS_VAR")) : PASS_VAR_DEFAULT;
+    switch (var & 3) {
+        case 0: return launch_edge_pass_var<MODE, 0>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st, skip_flag);
+        case 1: return launch_edge_pass_var<MODE, 1>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st, skip_flag);
+        case 2: return launch_edge_pass_var<MODE, 2>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st, skip_flag);
+        default: return launch_edge_pass_var<MODE, 3>(seg_ptr, seg_node, idx, B, G, lamT, out, n_seg, st, skip_flag);
+    }
 }
 
 // fused camera pass + cross-rank sum (see edge_pass_fused_kernel); Y needs no zeroing

@@ -248,11 +248,14 @@ class RotationResult:
 
 def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner: int = 200,
                     comm: Optional[Comm] = None, profile_events: bool = False, shortcut: bool = True,
-                    spanning_start: bool = True) -> RotationResult:
+                    spanning_start: bool = True, eval_gap: bool = False) -> RotationResult:
     """``shortcut=False`` forces the primal multiply through its two edge passes in every outer
     iteration (see ``vb_so3_stats.shortcut_outer``); ``spanning_start=False`` starts the first eigen-solve
     from identity blocks instead of the one-hop estimate around the gauge camera.  Both only change the
-    work done, not the result (agreement to rounding / to the eigen-solver's tolerance)."""
+    work done, not the result (agreement to rounding / to the eigen-solver's tolerance).
+    ``eval_gap=True`` also computes the reference's diagnostics in every outer iteration (the five
+    eigenvalues nearest zero, ``stats.evals_hist``) and applies its early exit ``max |lambda_1..5| <=
+    1e-6`` (bipgo.py:283-292), at the price of a second eigen-solve per iteration."""
     lib = _cabi.lib()
     dev = g.device
     if g.n_c < 3:
@@ -265,7 +268,7 @@ def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner:
         fn, fctx = comm.reducer(lib, 9 * g.n_c) if comm is not None else (None, None)
         fused = comm.peer if (comm is not None and comm.peer is not None and 9 * g.n_c <= comm.peer_capacity) else None
         opt = VbSo3Options(int(maxiter), int(max_inner), float(tol), fn, fctx, 1 if profile_events else 0,
-                           0 if shortcut else 1, 0 if spanning_start else 1, 0, fused)
+                           0 if shortcut else 1, 0 if spanning_start else 1, 1 if eval_gap else 0, fused)
         stats = VbSo3Stats()
         rc = lib.vb_so3sync_run(C.byref(g.cgraph), C.byref(opt), _ptr(r_c), _ptr(r_t), _ptr(ws), wsb,
                                 C.byref(stats), _stream())
