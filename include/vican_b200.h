@@ -173,7 +173,8 @@ int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64
  * sentinel tile_start[n_tiles] = E; tile_off [n_windows*n_c+1] = first tile of every run).  tile_cam /
  * tile_start must hold vb_ingest_max_tiles + 1 entries.
  * PADDING: t_B / c_B must be allocated for E + 2 blocks and t_cam / c_time for E + 8 indices
- * (the edge passes stream them with 16-byte granular bulk copies). */
+ * (the edge passes stream them with 16-byte granular bulk copies).
+ * WORKSPACE of vb_ingest_build: vb_ingest_workspace_bytes(max(n_raw, vb_ingest_windows(...) * n_c + 1)). */
 int64_t vb_ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len);
 int64_t vb_ingest_windows(int64_t n_edges, int64_t n_c, int64_t tile_len);
 int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* marker, const double* R,
@@ -185,6 +186,15 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_off,
                     int64_t* h_n_tiles, double* deg_t, double* deg_c, void* workspace,
                     int64_t workspace_bytes, void* stream);
+
+/* Incremental ingestion (streamed detections, cam.py:176-185, :243-263): a chunk of NEW time nodes is ingested
+ * on its own (vb_ingest_sort / vb_ingest_build with chunk-local time indices) and appended behind the arrays
+ * of the growing graph -- the time-sorted CSR is append-only in time, and the chunk's time windows become new
+ * windows of the camera-pass order, so nothing already resident is re-sorted or rewritten.  These two helpers
+ * do the index fix-ups: dst[i] = src[i] + add (row pointers, edge / tile / time offsets) and dst += src (camera
+ * degrees).  Block and weight arrays are appended with plain device-to-device copies by the caller. */
+int vb_offset_copy_i32(int32_t* dst, const int32_t* src, int64_t n, int32_t add, void* stream);
+int vb_add_inplace_f64(double* dst, const double* src, int64_t n, void* stream);
 
 /* ---- rotation stage (bipgo.py:243-348) --------------------------------------------------- */
 /* One edge pass each (exposed for tests and for the roofline measurement).  Gathered node

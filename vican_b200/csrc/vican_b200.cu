@@ -174,9 +174,10 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     double* deg_c, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_raw <= 0 || n_pairs <= 0 || tile_len <= 0) return VB_STATUS_BAD_ARGUMENT;
-    IngestWork w = carve_ingest(workspace, n_raw);
-    if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     const int64_t E = n_pairs;
+    const int64_t n_seg_ws = ingest_windows(E, n_c, tile_len) * n_c + 1;   // a chunk can hold fewer detections than cameras
+    IngestWork w = carve_ingest(workspace, n_raw > n_seg_ws ? n_raw : n_seg_ws);
+    if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     pair_start_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(raw_pair, pair_start, n_raw, E);
     fold_aggregate_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(cam, time, marker, R, k_r, k_t, markerC, round_kr_f32,
                                                               raw_perm, pair_start, E, t_cam, t_time, t_B, t_a, t_w);
@@ -186,7 +187,6 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     // camera-pass copy of the blocks: (time window, camera, time) order, tiles = runs of (window, camera)
     const int64_t n_win = ingest_windows(E, n_c, tile_len);
     const int64_t n_seg = n_win * n_c;
-    if (n_seg + 1 > n_raw + 1) return VB_STATUS_BAD_ARGUMENT;
     make_window_keys_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, t_time, n_c, n_t, n_win, w.keys_a, w.vals_a, E);
     size_t tb = w.cub_bytes;
     VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
@@ -206,6 +206,32 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     const int64_t n_tiles = (int64_t)last_off;
     *h_n_tiles = n_tiles;
     count_launches(12);   // pair_start, fold, seg_ptr x2, seg_sum, window keys, window_seg, cam_runs_sum, gather, tile_count, tile_fill
+    return 0;
+}
+
+// dst[i] = src[i] + add: appends an index array of a freshly ingested chunk behind the arrays of a growing graph
+__global__ void offset_copy_kernel(int* __restrict__ dst, const int* __restrict__ src, int64_t n, int add) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
+__global__ void add_inplace_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+int vb_offset_copy_i32(int32_t* dst, const int32_t* src, int64_t n, int32_t add, void* stream) {
+    if (n <= 0) return 0;
+    offset_copy_kernel<<<ing_grid(n), ING_THREADS, 0, (cudaStream_t)stream>>>(dst, src, n, add);
+    VB_KERNEL_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int vb_add_inplace_f64(double* dst, const double* src, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    add_inplace_kernel<<<ing_grid(n), ING_THREADS, 0, (cudaStream_t)stream>>>(dst, src, n);
+    VB_KERNEL_CHECK();
+    count_launches(1);
     return 0;
 }
 

@@ -168,6 +168,9 @@ class DeviceGraph:
             self.t_a, self.t_w = e(E, F64), e(E, F64)
             self.pair_start = e(E + 1, I32)
             self.n_windows = int(lib.vb_ingest_windows(E, self.n_c, tl))
+            if self.n_windows * self.n_c + 1 > n_raw:     # tiny chunk: fewer detections than (window, camera) runs
+                wsb = int(lib.vb_ingest_workspace_bytes(self.n_windows * self.n_c + 1))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             self.c_segptr = e(self.n_windows * self.n_c + 1, I32)
             self.c_w, self.c_order = e(E, F64), e(E, I32)
             self.tile_cam, self.tile_start = e(max_tiles + 1, I32), e(max_tiles + 1, I32)
@@ -231,6 +234,117 @@ class DeviceGraph:
         if kind == "cam":      # blocks + time index, tile table, W gather source (padded), Y accumulate
             return 76 * E + (8 + 2 * 72) * self.n_tiles + 96 * n_t + 72 * n_c
         raise ValueError(kind)
+
+
+class StreamingGraph:
+    """Device graph that grows by ranges of NEW time nodes (the caller side of the path,
+    ``estimate_pose_mp`` output arriving image by image, cam.py:176-185, :243-263).
+
+    ``append`` ingests one chunk on its own (same kernels as ``DeviceGraph``, chunk-local time indices)
+    and places its arrays behind the resident ones: the time-sorted block-CSR is append-only in time, and
+    the chunk's time windows become new windows of the camera-pass order, so nothing already on the device
+    is re-sorted or rewritten -- only index offsets are added (``vb_offset_copy_i32``) and the camera
+    degrees accumulated (``vb_add_inplace_f64``).  Cost per append is proportional to the chunk.
+    ``graph()`` returns a ``DeviceGraph`` view of the current state for ``solve_rotations`` /
+    ``solve_translations``; ``t`` are the detections' translations in raw order.  Storage grows by
+    doubling.  A chunk should hold a few thousand detections (one chunk = at least one camera-pass
+    window: ``io.EdgeAccumulator`` does the host-side batching)."""
+
+    _I32 = ("t_cam", "t_time", "t_rowptr", "pair_start", "c_time", "c_order", "c_segptr", "tile_cam", "tile_start",
+            "tile_off", "cam", "time", "marker", "raw_perm", "raw_pair")
+
+    def __init__(self, n_c: int, markerC, device=None, round_kr_f32: bool = False, capacity_edges: int = 1 << 16):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_c = int(n_c)
+        self.markerC = _dev(markerC, F64, self.device).reshape(-1, 9)
+        self.round_kr_f32 = bool(round_kr_f32)
+        self.n_t = self.n_edges = self.n_raw = self.n_tiles = self.n_windows = 0
+        self._cap0 = int(capacity_edges)
+        self._a = {}
+        z = lambda n, dt, w=None: torch.zeros((n,) if w is None else (n, w), dtype=dt, device=self.device)  # noqa: E731
+        self._a["deg_c"] = z(self.n_c, F64)
+        for name in self._I32:
+            self._a[name] = z(1, I32)
+        for name, w in (("t_B", 9), ("c_B", 9), ("t_a", None), ("t_w", None), ("c_w", None), ("deg_t", None),
+                        ("k_r", None), ("k_t", None), ("t", 3)):
+            self._a[name] = z(1, F64, w)
+
+    def _need(self, name, n):
+        """Make array ``name`` hold at least ``n`` leading entries (amortised doubling, old content kept)."""
+        a = self._a[name]
+        if a.shape[0] >= n:
+            return a
+        cap = max(n, 2 * a.shape[0], self._cap0)
+        b = torch.zeros((cap,) + tuple(a.shape[1:]), dtype=a.dtype, device=self.device)
+        b[:a.shape[0]] = a
+        self._a[name] = b
+        return b
+
+    def append(self, cam, time_local, marker, R, t, k_r, k_t, n_t_chunk: int) -> None:
+        """Detections of ``n_t_chunk`` new time nodes; ``time_local`` counts from 0 inside the chunk (global
+        index = current ``n_t`` + local)."""
+        lib = _cabi.lib()
+        c = DeviceGraph(cam, time_local, marker, R, k_r, k_t, self.markerC, self.n_c, int(n_t_chunk),
+                        round_kr_f32=self.round_kr_f32, device=self.device)
+        E0, N0, R0, T0, W0 = self.n_edges, self.n_t, self.n_raw, self.n_tiles, self.n_windows
+        Ec, Nc, Rc, Tc, Wc, n_c = c.n_edges, c.n_t, c.n_raw, c.n_tiles, c.n_windows, self.n_c
+        with torch.cuda.device(self.device):
+            def put(name, src, lo):                       # plain device-to-device append
+                self._need(name, lo + src.shape[0] + (8 if name in ("t_cam", "c_time") else 2 if name in ("t_B", "c_B") else 0))
+                self._a[name][lo:lo + src.shape[0]] = src
+
+            def put_off(name, src, lo, add):              # append with an index offset (one small kernel)
+                dst = self._need(name, lo + src.shape[0] + (8 if name in ("t_cam", "c_time") else 0))
+                check(lib.vb_offset_copy_i32(C.c_void_p(dst.data_ptr() + 4 * lo), _ptr(src), src.shape[0], int(add), _stream()),
+                      "vb_offset_copy_i32")
+            put("t_B", c.t_B, E0); put("c_B", c.c_B, E0)
+            put("t_a", c.t_a, E0); put("t_w", c.t_w, E0); put("c_w", c.c_w, E0)
+            put("deg_t", c.deg_t, N0)
+            put("k_r", c.k_r, R0); put("k_t", c.k_t, R0); put("t", _dev(t, F64, self.device).reshape(-1, 3), R0)
+            put("cam", c.cam, R0); put("marker", c.marker, R0); put("t_cam", c.t_cam, E0)
+            put("tile_cam", c.tile_cam[:Tc], T0)
+            put_off("t_time", c.t_time, E0, N0)
+            put_off("t_rowptr", c.t_rowptr, N0, E0)
+            put_off("pair_start", c.pair_start, E0, R0)
+            put_off("c_time", c.c_time, E0, N0)
+            put_off("c_order", c.c_order, E0, E0)
+            put_off("c_segptr", c.c_segptr, W0 * n_c, E0)
+            put_off("tile_start", c.tile_start[:Tc + 1], T0, E0)
+            put_off("tile_off", c.tile_off, W0 * n_c, T0)
+            put_off("time", c.time, R0, N0)
+            put_off("raw_perm", c.raw_perm, R0, R0)
+            put_off("raw_pair", c.raw_pair, R0, E0)
+            check(lib.vb_add_inplace_f64(_ptr(self._a["deg_c"]), _ptr(c.deg_c), n_c, _stream()), "vb_add_inplace_f64")
+        self.n_edges, self.n_t, self.n_raw, self.n_tiles, self.n_windows = E0 + Ec, N0 + Nc, R0 + Rc, T0 + Tc, W0 + Wc
+
+    @property
+    def t(self) -> torch.Tensor:
+        return self._a["t"][:self.n_raw]
+
+    def graph(self) -> "DeviceGraph":
+        """``DeviceGraph`` view of the current state (shares storage with this object)."""
+        g = DeviceGraph.__new__(DeviceGraph)
+        a, E, N, Rn, T, W = self._a, self.n_edges, self.n_t, self.n_raw, self.n_tiles, self.n_windows
+        if E == 0:
+            raise ValueError("no detections appended yet")
+        g.device, g.n_c, g.n_t, g.n_edges, g.n_raw, g.n_tiles, g.n_windows = self.device, self.n_c, N, E, Rn, T, W
+        g.tile_len = None
+        self._need("t_cam", E + 8); self._need("c_time", E + 8); self._need("t_B", E + 2); self._need("c_B", E + 2)
+        a = self._a
+        for name, n in (("t_cam", E), ("t_time", E), ("t_B", E), ("t_a", E), ("t_w", E), ("c_time", E), ("c_B", E), ("c_w", E),
+                        ("c_order", E), ("t_rowptr", N + 1), ("pair_start", E + 1), ("c_segptr", W * self.n_c + 1),
+                        ("tile_cam", T), ("tile_start", T + 1), ("tile_off", W * self.n_c + 1), ("deg_t", N),
+                        ("cam", Rn), ("time", Rn), ("marker", Rn), ("k_r", Rn), ("k_t", Rn), ("raw_perm", Rn), ("raw_pair", Rn)):
+            setattr(g, name, a[name][:n])
+        g.deg_c = a["deg_c"]
+        g.tile_part = torch.empty((max(T, 1), 9), dtype=F64, device=self.device)
+        g.cgraph = VbGraph(
+            g.n_c, N, E, T, W, g.t_rowptr.data_ptr(), g.t_cam.data_ptr(), g.t_B.data_ptr(), g.t_w.data_ptr(),
+            g.c_segptr.data_ptr(), g.c_order.data_ptr(), g.c_time.data_ptr(), g.c_B.data_ptr(), g.c_w.data_ptr(),
+            g.tile_cam.data_ptr(), g.tile_start.data_ptr(), g.tile_off.data_ptr(), g.tile_part.data_ptr(),
+            g.deg_t.data_ptr(), g.deg_c.data_ptr(), 0, 0, 0, 0, 0, 0)
+        g._sell = None
+        return g
 
 
 @dataclasses.dataclass
