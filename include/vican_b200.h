@@ -228,11 +228,12 @@ int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, do
 /* Per aggregated pair g_p = sum_{raw e in p} k_t^2 d_e with
  *   d_e = Rw_c t_cm + Rw_t q_m,  q_m = (R_0^T R_m) (T_m^-1 T_0).t   (bipgo.py:451-455),
  * Rw = world rotations (transposes of r_c / r_t).  Also writes d_raw [n_raw][3] in sorted order
- * when non-NULL (needed by LSQR).  rhs = J^T t~ : rhs_c [n_c][3] (caller zeroes), rhs_t [n_t][3]. */
+ * when non-NULL (needed by LSQR).  rhs = J^T t~ : rhs_c [n_c][3], rhs_t [n_t][3].  r_c_pad: scratch
+ * [n_c][vb_gather_stride()] (the camera rotations are gathered from a padded copy with 256-bit loads). */
 int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
                  const double* t_cm, const double* k_t, const double* marker_q, const double* r_c,
                  const double* r_t, const int32_t* t_time, double* pair_g,
-                 double* d_sorted, double* rhs_c, double* rhs_t, void* stream);
+                 double* d_sorted, double* rhs_c, double* rhs_t, double* r_c_pad, void* stream);
 /* Sliced-ELL copy of the translation Laplacian for vb_trans_cg (see vb_graph).  vb_sell_count writes the slice
  * pointers (st_ptr [ceil(n_t/8)+2], sc_ptr [ceil(n_c/8)+2]) and returns the chunk totals on the host
  * (synchronises); the caller allocates 32 * chunks slots per side and vb_sell_fill fills them. */

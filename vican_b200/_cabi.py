@@ -87,7 +87,7 @@ SIGNATURES = {
     "vb_so3sync_workspace_bytes": (I64, [I64, I64]),
     "vb_so3sync_run": (C.c_int, [C.POINTER(VbGraph), C.POINTER(VbSo3Options), VP, VP, VP, I64,
                                  C.POINTER(VbSo3Stats), VP]),
-    "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+    "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "vb_trans_cg_workspace_bytes": (I64, [I64, I64]),
     "vb_sell_workspace_bytes": (I64, [I64, I64]),
     "vb_sell_count": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, c_i64p, VP, I64, VP]),

@@ -7,11 +7,31 @@
 // Key sorting uses CUB's device radix sort (index plumbing, not arithmetic).
 #pragma once
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "../../include/vican_b200.h"
 #include "common.cuh"
 
 namespace vb {
+
+// 1 where sorted position i starts a new (time, camera) pair, 0 at i = 0: the inclusive scan of these flags is
+// the pair id of every position (fed to CUB's scan through a transform iterator: no flag array, no extra pass)
+struct HeadFlagCT {
+    const int* time; const int* cam;
+    __host__ __device__ int operator()(int i) const { return (i > 0 && (time[i] != time[i - 1] || cam[i] != cam[i - 1])) ? 1 : 0; }
+};
+struct HeadFlagKey {
+    const uint64_t* keys;
+    __host__ __device__ int operator()(int i) const { return (i > 0 && keys[i] != keys[i - 1]) ? 1 : 0; }
+};
+
+__global__ void check_sorted_ct_kernel(const int* __restrict__ time, const int* __restrict__ cam, int64_t n, int* __restrict__ unsorted_flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const int t0 = time[i], t1 = time[i + 1];
+    if (t0 > t1 || (t0 == t1 && cam[i] > cam[i + 1])) *unsorted_flag = 1;
+}
 
 constexpr int ING_THREADS = 256;
 inline int ing_grid(int64_t n) { return (int)((n + ING_THREADS - 1) / ING_THREADS); }
@@ -87,6 +107,99 @@ __global__ void fold_aggregate_kernel(const int* __restrict__ cam, const int* __
     for (int i = 0; i < 9; ++i) t_B[9 * p + i] = B[i];
     t_a[p] = a;
     t_w[p] = w;
+}
+
+// Per aggregated pair: its endpoints and its key in the camera-pass order, key = window(time) * n_c + cam
+// (32-bit: n_windows * n_c is a few hundred thousand).  The pairs are already sorted by (time, camera) and the
+// radix sort is stable, so sorting by this key orders them by (window, camera, time).  Tiles of all cameras
+// that fall in the same time window are adjacent in the stream, so the W records gathered by concurrently
+// running warps of the camera pass come from one window of W (L2 resident) instead of all of it.
+__global__ void pair_keys_kernel(const int* __restrict__ cam, const int* __restrict__ time, const int* __restrict__ raw_perm,
+                                 const int* __restrict__ pair_start, int64_t n_pairs, int64_t n_c, int64_t n_t, int64_t n_win,
+                                 int* __restrict__ t_cam, int* __restrict__ t_time, uint32_t* __restrict__ keys,
+                                 int* __restrict__ vals) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int64_t r0 = raw_perm[pair_start[p]];
+    const int c = cam[r0], t = time[r0];
+    t_cam[p] = c;
+    t_time[p] = t;
+    const uint64_t win = (uint64_t)t * (uint64_t)n_win / (uint64_t)n_t;
+    keys[p] = (uint32_t)(win * (uint64_t)n_c + (uint64_t)c);
+    vals[p] = (int)p;
+}
+
+// c_pos[c_order[i]] = i : where every time-sorted pair sits in the camera-pass order
+__global__ void inverse_perm_kernel(const int* __restrict__ c_order, int* __restrict__ c_pos, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) c_pos[c_order[i]] = (int)i;
+}
+
+// Fold + aggregate (bipgo.py:209-221) writing BOTH copies of the blocks from the same registers: the
+// time-sorted block-CSR (t_B, coalesced through a shared-memory transpose) and the camera-pass copy (c_B,
+// stored transposed, one contiguous 72-byte record per pair at its camera-pass position), plus the
+// per-pair weights in both orders.  One thread folds one pair, in original detection order.
+constexpr int FOLD_THREADS = 256;
+__global__ void __launch_bounds__(FOLD_THREADS)
+fold_both_kernel(const int* __restrict__ marker, const double* __restrict__ R, const double* __restrict__ k_r,
+                 const double* __restrict__ k_t, const double* __restrict__ markerC, int round_f32,
+                 const int* __restrict__ raw_perm, const int* __restrict__ pair_start, int64_t n_pairs,
+                 const int* __restrict__ t_time, const int* __restrict__ c_pos, double* __restrict__ t_B,
+                 double* __restrict__ t_a, double* __restrict__ t_w, double* __restrict__ c_B, int* __restrict__ c_time,
+                 double* __restrict__ c_w) {
+    __shared__ double sB[FOLD_THREADS * 9];
+    __shared__ double sW[FOLD_THREADS];
+    __shared__ int sPos[FOLD_THREADS], sTime[FOLD_THREADS];
+    const int64_t p0 = (int64_t)blockIdx.x * FOLD_THREADS;
+    const int64_t p = p0 + threadIdx.x;
+    if (p < n_pairs) {
+        const int s = pair_start[p], e = pair_start[p + 1];
+        double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double a = 0.0, w = 0.0;
+        for (int pos = s; pos < e; ++pos) {
+            const int64_t r = raw_perm[pos];
+            const double kr = k_r[r], kt = k_t[r];
+            double kR[9], Cm[9], blk[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const double v = R[9 * r + i];
+                kR[i] = round_f32 ? (double)((float)kr * (float)v) : kr * v;
+                Cm[i] = markerC[9 * (int64_t)marker[r] + i];
+            }
+            mm3(kR, Cm, blk);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) B[i] += blk[i];
+            a += kr;
+            w += kt * kt;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sB[9 * threadIdx.x + i] = B[i];
+        t_a[p] = a;
+        t_w[p] = w;
+        sW[threadIdx.x] = w;
+        sPos[threadIdx.x] = c_pos[p];
+        sTime[threadIdx.x] = t_time[p];
+    }
+    __syncthreads();
+    const int n_here = (int)((n_pairs - p0) < FOLD_THREADS ? (n_pairs - p0) : FOLD_THREADS);
+    // time-sorted copy: the CTA's 256 x 9 doubles are contiguous in t_B
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const int i = q * FOLD_THREADS + threadIdx.x;
+        if (i < 9 * n_here) t_B[9 * p0 + i] = sB[i];
+    }
+    // camera-pass copy: 9 consecutive threads write one pair's record, transposed
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const int i = q * FOLD_THREADS + threadIdx.x;
+        const int pl = i / 9, k = i - 9 * pl;
+        if (pl < n_here) {
+            const int64_t dst = sPos[pl];
+            c_B[9 * dst + k] = sB[9 * pl + 3 * (k % 3) + k / 3];
+            if (k == 0) c_time[dst] = sTime[pl];
+            if (k == 1) c_w[dst] = sW[pl];
+        }
+    }
 }
 
 __global__ void check_sorted_kernel(const uint64_t* __restrict__ keys, int64_t n, int* __restrict__ unsorted_flag) {
@@ -243,35 +356,33 @@ inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n
     if (n_raw <= 0) return VB_STATUS_BAD_ARGUMENT;
     IngestWork w = carve_ingest(workspace, n_raw);
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
-    make_keys_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(time, cam, n_c, w.keys_a, w.vals_a, n_raw);
-    VB_KERNEL_CHECK();
     // adaptive: detections that already arrive ordered by (time, camera) -- the usual layout of a
-    // recording -- skip the radix sort (one 8-byte pass instead of five 24-byte passes)
+    // recording -- skip the key build and the radix sort altogether
     VB_CHECK(cudaMemsetAsync(w.tmp_a, 0, sizeof(int), st));
-    check_sorted_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(w.keys_a, n_raw, w.tmp_a);
+    check_sorted_ct_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(time, cam, n_raw, w.tmp_a);
     int unsorted = 0;
     VB_CHECK(cudaMemcpyAsync(&unsorted, w.tmp_a, sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CHECK(cudaStreamSynchronize(st));
     size_t tb = w.cub_bytes;
-    const uint64_t* keys_sorted = w.keys_a;
+    thrust::counting_iterator<int> iota(0);
     if (unsorted) {
+        make_keys_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(time, cam, n_c, w.keys_a, w.vals_a, n_raw);
         VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
                                                  raw_perm, (int)n_raw, 0, key_bits(n_c, n_t), st));
-        keys_sorted = w.keys_b;
+        tb = w.cub_bytes;
+        auto flags = thrust::make_transform_iterator(iota, HeadFlagKey{w.keys_b});
+        VB_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, flags, raw_pair, (int)n_raw, st));
     } else {
         iota_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(raw_perm, n_raw);
+        auto flags = thrust::make_transform_iterator(iota, HeadFlagCT{time, cam});
+        VB_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, flags, raw_pair, (int)n_raw, st));
     }
-    head_flags_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(keys_sorted, w.tmp_a, n_raw);
-    VB_KERNEL_CHECK();
-    tb = w.cub_bytes;
-    VB_CHECK(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, (const int*)w.tmp_a, w.tmp_b, (int)n_raw, st));
-    pair_ids_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(w.tmp_b, raw_pair, n_raw);
     VB_KERNEL_CHECK();
     int last = 0;
-    VB_CHECK(cudaMemcpyAsync(&last, w.tmp_b + (n_raw - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    VB_CHECK(cudaMemcpyAsync(&last, raw_pair + (n_raw - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CHECK(cudaStreamSynchronize(st));
-    *h_n_pairs = last;
-    count_launches(5);   // make_keys, check_sorted, iota (sorted input) or CUB's sort, head_flags, pair_ids
+    *h_n_pairs = (int64_t)last + 1;
+    count_launches(unsorted ? 2 : 2);   // check_sorted + (make_keys | iota); CUB's sort / scan are library kernels
     return 0;
 }
 

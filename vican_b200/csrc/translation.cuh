@@ -28,15 +28,20 @@ inline int tr_warp_grid(int64_t n_warps) { return (int)((n_warps * 32 + TR_THREA
 __global__ void trans_pair_kernel(const int* __restrict__ raw_perm, const int* __restrict__ pair_start,
                                   const int* __restrict__ marker, const double* __restrict__ t_cm,
                                   const double* __restrict__ k_t, const double* __restrict__ marker_q,
-                                  const double* __restrict__ r_c, const double* __restrict__ r_t,
+                                  const double* __restrict__ r_c_pad, const double* __restrict__ r_t,
                                   const int* __restrict__ t_cam, const int* __restrict__ t_time, int64_t n_pairs,
                                   double* __restrict__ pair_g, double* __restrict__ d_sorted) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     double Rc[9], Rt[9];
     const int64_t c = t_cam[p], t = t_time[p];
+    // camera rotation: three 256-bit row loads from the padded copy (every lane reads another camera: one L1
+    // wavefront per load and lane instead of nine); time rotation: neighbouring pairs share the node
+    ld_row256(r_c_pad + GSTRIDE * c, Rc[0], Rc[1], Rc[2]);
+    ld_row256(r_c_pad + GSTRIDE * c + 4, Rc[3], Rc[4], Rc[5]);
+    ld_row256(r_c_pad + GSTRIDE * c + 8, Rc[6], Rc[7], Rc[8]);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { Rc[i] = r_c[9 * c + i]; Rt[i] = r_t[9 * t + i]; }
+    for (int i = 0; i < 9; ++i) Rt[i] = r_t[9 * t + i];
     double g0 = 0, g1 = 0, g2 = 0;
     for (int pos = pair_start[p]; pos < pair_start[p + 1]; ++pos) {
         const int64_t r = raw_perm[pos];

@@ -179,22 +179,26 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     IngestWork w = carve_ingest(workspace, n_raw > n_seg_ws ? n_raw : n_seg_ws);
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     pair_start_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(raw_pair, pair_start, n_raw, E);
-    fold_aggregate_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(cam, time, marker, R, k_r, k_t, markerC, round_kr_f32,
-                                                              raw_perm, pair_start, E, t_cam, t_time, t_B, t_a, t_w);
-    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_time, nullptr, t_rowptr, E, n_t);
-    seg_sum_kernel<<<ing_grid(n_t * 32), ING_THREADS, 0, st>>>(t_rowptr, nullptr, t_a, deg_t, n_t);
-    VB_KERNEL_CHECK();
-    // camera-pass copy of the blocks: (time window, camera, time) order, tiles = runs of (window, camera)
+    // camera-pass order first ((time window, camera, time); tiles = runs of (window, camera)), so that the fold can
+    // write both copies of the blocks in one pass over the detections
     const int64_t n_win = ingest_windows(E, n_c, tile_len);
     const int64_t n_seg = n_win * n_c;
-    make_window_keys_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_cam, t_time, n_c, n_t, n_win, w.keys_a, w.vals_a, E);
+    uint32_t* keys32_a = (uint32_t*)w.keys_a;
+    uint32_t* keys32_b = (uint32_t*)w.keys_b;
+    int* c_pos = w.tmp_a;
+    pair_keys_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(cam, time, raw_perm, pair_start, E, n_c, n_t, n_win, t_cam, t_time,
+                                                         keys32_a, w.vals_a);
     size_t tb = w.cub_bytes;
-    VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint64_t*)w.keys_a, w.keys_b, (const int*)w.vals_a,
+    VB_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, (const uint32_t*)keys32_a, keys32_b, (const int*)w.vals_a,
                                              c_order, (int)E, 0, key_bits(n_c, n_win), st));
-    window_seg_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.keys_b, w.tmp_a, E);
-    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(w.tmp_a, nullptr, c_segptr, E, n_seg);
+    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>((const int*)keys32_b, nullptr, c_segptr, E, n_seg);
+    inverse_perm_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(c_order, c_pos, E);
+    fold_both_kernel<<<(int)((E + FOLD_THREADS - 1) / FOLD_THREADS), FOLD_THREADS, 0, st>>>(
+        marker, R, k_r, k_t, markerC, round_kr_f32, raw_perm, pair_start, E, t_time, c_pos, t_B, t_a, t_w, c_B, c_time, c_w);
+    seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_time, nullptr, t_rowptr, E, n_t);
+    seg_sum_kernel<<<ing_grid(n_t * 32), ING_THREADS, 0, st>>>(t_rowptr, nullptr, t_a, deg_t, n_t);
     cam_runs_sum_kernel<<<ing_grid(n_c * 32), ING_THREADS, 0, st>>>(c_segptr, n_win, n_c, c_order, t_a, deg_c);
-    gather_cam_sorted_kernel<<<ing_grid(9 * E), ING_THREADS, 0, st>>>(c_order, t_time, t_B, t_w, c_time, c_B, c_w, E);
+    VB_KERNEL_CHECK();
     tile_count_kernel<<<ing_grid(n_seg + 1), ING_THREADS, 0, st>>>(c_segptr, w.tmp_c, n_seg, (int)tile_len);
     tb = w.cub_bytes;
     VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.tmp_c, tile_off, (int)(n_seg + 1), st));
@@ -205,7 +209,7 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     VB_CHECK(cudaStreamSynchronize(st));
     const int64_t n_tiles = (int64_t)last_off;
     *h_n_tiles = n_tiles;
-    count_launches(12);   // pair_start, fold, seg_ptr x2, seg_sum, window keys, window_seg, cam_runs_sum, gather, tile_count, tile_fill
+    count_launches(10);   // pair_start, pair_keys, seg_ptr x2, inverse_perm, fold_both, seg_sum, cam_runs_sum, tile_count, tile_fill
     return 0;
 }
 
@@ -283,18 +287,20 @@ int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, do
 // ---------------------------------------------------------------------------- translation
 int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
                  const double* t_cm, const double* k_t, const double* marker_q, const double* r_c, const double* r_t,
-                 const int32_t* t_time, double* pair_g, double* d_sorted, double* rhs_c, double* rhs_t, void* stream) {
+                 const int32_t* t_time, double* pair_g, double* d_sorted, double* rhs_c, double* rhs_t, double* r_c_pad,
+                 void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t E = g->n_edges;
-    if (E <= 0) return VB_STATUS_BAD_ARGUMENT;
-    trans_pair_kernel<<<tr_grid(E), TR_THREADS, 0, st>>>(raw_perm, pair_start, marker, t_cm, k_t, marker_q, r_c, r_t,
+    if (E <= 0 || r_c_pad == nullptr) return VB_STATUS_BAD_ARGUMENT;
+    { int rc = launch_pad_blocks(r_c, r_c_pad, g->n_c, st); if (rc) return rc; }
+    trans_pair_kernel<<<tr_grid(E), TR_THREADS, 0, st>>>(raw_perm, pair_start, marker, t_cm, k_t, marker_q, r_c_pad, r_t,
                                                         g->t_cam, t_time, E, pair_g, d_sorted);
     VB_CHECK(cudaMemsetAsync(rhs_c, 0, 3 * g->n_c * sizeof(double), st));
     VB_CHECK(cudaMemsetAsync(rhs_t, 0, 3 * g->n_t * sizeof(double), st));
     seg_sum3_kernel<<<tr_warp_grid(g->n_t), TR_THREADS, 0, st>>>(g->t_rowptr, nullptr, pair_g, 1.0, rhs_t, g->n_t);
     cam_runs_sum3_kernel<<<tr_warp_grid(g->n_c), TR_THREADS, 0, st>>>(g->c_segptr, g->n_windows, g->n_c, g->c_order, pair_g, -1.0, rhs_c);
     VB_KERNEL_CHECK();
-    count_launches(3);
+    count_launches(4);
     return 0;
 }
 

@@ -422,9 +422,10 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
         d_sorted = torch.empty((g.n_raw, 3), dtype=F64, device=dev) if need_rows else None
         rhs_c = torch.empty((g.n_c, 3), dtype=F64, device=dev)
         rhs_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
+        r_c_pad = torch.empty((g.n_c, int(lib.vb_gather_stride())), dtype=F64, device=dev)
         check(lib.vb_trans_rhs(C.byref(g.cgraph), _ptr(g.raw_perm), _ptr(g.pair_start), _ptr(g.marker), _ptr(t_cm),
                                _ptr(g.k_t), _ptr(marker_q), _ptr(rot.r_c), _ptr(rot.r_t), _ptr(g.t_time),
-                               _ptr(pair_g), _ptr(d_sorted), _ptr(rhs_c), _ptr(rhs_t), _stream()),
+                               _ptr(pair_g), _ptr(d_sorted), _ptr(rhs_c), _ptr(rhs_t), _ptr(r_c_pad), _stream()),
               "vb_trans_rhs")
         x_c = torch.empty((g.n_c, 3), dtype=F64, device=dev)
         x_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
