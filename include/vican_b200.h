@@ -187,6 +187,12 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int64_t* h_n_tiles, double* deg_t, double* deg_c, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
+/* Number of connected components of the bipartite graph of aggregated edges (min-label hooking + pointer
+ * jumping on the device).  labels: scratch [n_c + n_t + 2] int32; t_time [E] = time node of every time-sorted
+ * edge.  The reference's early exit `max |lambda_1..5| <= 1e-6` (bipgo.py:283) can only fire with > 1 component.
+ * Synchronises the stream. */
+int vb_count_components(const vb_graph* g, const int32_t* t_time, int32_t* labels, int64_t* h_count, void* stream);
+
 /* Incremental ingestion (streamed detections, cam.py:176-185, :243-263): a chunk of NEW time nodes is ingested
  * on its own (vb_ingest_sort / vb_ingest_build with chunk-local time indices) and appended behind the arrays
  * of the growing graph -- the time-sorted CSR is append-only in time, and the chunk's time windows become new

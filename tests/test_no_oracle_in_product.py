@@ -18,9 +18,11 @@ def test_product_package_never_imports_oracle():
 
 
 def test_bench_uses_oracle_only_for_cpu_legs():
+    """bench.py may run the oracle only as the CPU baseline: in cpu_sample_solve (cpu_baseline / --impl reference
+    legs) and in configs_block (the CPU port timed next to the drop-in on the same dictionaries)."""
     src = open(os.path.join(ROOT, "bench.py")).read()
     uses = [m.start() for m in re.finditer(r"from oracle import", src)]
-    assert len(uses) == 1
-    # the single import lives in cpu_sample_solve (cpu_baseline / --impl reference legs)
-    fn_start = src.rfind("def ", 0, uses[0])
-    assert src[fn_start:].startswith("def cpu_sample_solve")
+    assert len(uses) == 2
+    for u in uses:
+        fn_start = src.rfind("\ndef ", 0, u) + 1
+        assert src[fn_start:].startswith(("def cpu_sample_solve", "def configs_block")), src[fn_start:fn_start + 40]

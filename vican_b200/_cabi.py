@@ -75,6 +75,7 @@ SIGNATURES = {
     "vb_ingest_build": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, I64, C.c_int, VP, VP, I64, I64, I64, I64,
                                   VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, c_i64p, VP, VP,
                                   VP, I64, VP]),
+    "vb_count_components": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, VP]),
     "vb_offset_copy_i32": (C.c_int, [VP, VP, I64, I32, VP]),
     "vb_add_inplace_f64": (C.c_int, [VP, VP, I64, VP]),
     "vb_gather_stride": (C.c_int, []),

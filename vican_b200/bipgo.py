@@ -149,16 +149,6 @@ class EigenConvergenceWarning(RuntimeWarning):
     tolerance (the reference's ARPACK call raises ArpackNoConvergence in that situation)."""
 
 
-def _n_components(tab: EdgeTable) -> int:
-    """Connected components of the bipartite detection graph (host, scipy csgraph: plumbing)."""
-    import scipy.sparse as sp
-    from scipy.sparse.csgraph import connected_components
-    n_c, n_t = tab.n_c, tab.n_t
-    adj = sp.coo_matrix((np.ones(tab.n_raw, dtype=np.int8), (tab.cam_idx, n_c + tab.time_idx.astype(np.int64))),
-                        shape=(n_c + n_t, n_c + n_t))
-    return int(connected_components(adj, directed=False, return_labels=False))
-
-
 def _solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: Optional[str], mode: str = "parity",
                  tol: float = 1e-13, strict: bool = False, verbose: bool = False):
     t0 = _time.perf_counter()
@@ -171,7 +161,7 @@ def _solve_table(tab: EdgeTable, maxiter: int, lsqr_solver: Optional[str], mode:
     # (bipgo.py:283-292).  lambda_4, lambda_5 are O(degree) on a connected graph, so the test can only fire when
     # the graph falls apart into components: only then (or for verbose callers, who get the reference's
     # evals / eigengap read-out) is the second eigen-solve per iteration paid for.
-    n_comp = _n_components(tab)
+    n_comp = g.n_components()
     if n_comp > 1:
         warnings.warn("the detection graph has %d connected components: poses outside the gauge camera's component "
                       "are undetermined (the reference returns an arbitrary member of a 3 x %d dimensional "

@@ -313,6 +313,30 @@ __global__ void cam_runs_sum_kernel(const int* __restrict__ segptr, int64_t n_wi
     if (lane == 0) out[c] = acc;
 }
 
+// Connected components of the bipartite graph (cameras 0 .. n_c-1, time nodes n_c ..): min-label hooking over
+// the aggregated edges + pointer jumping until nothing changes (a handful of rounds: the graph has a small
+// diameter).  The reference's early exit (bipgo.py:283) can only fire when there is more than one component.
+__global__ void cc_hook_kernel(const int* __restrict__ t_cam, const int* __restrict__ t_time, int64_t n_edges, int n_c,
+                               int* __restrict__ label, int* __restrict__ changed) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int u = t_cam[e], v = n_c + t_time[e];
+    const int lu = label[u], lv = label[v];
+    if (lu < lv) { atomicMin(label + lv, lu); atomicMin(label + v, lu); *changed = 1; }
+    else if (lv < lu) { atomicMin(label + lu, lv); atomicMin(label + u, lv); *changed = 1; }
+}
+__global__ void cc_jump_kernel(int* __restrict__ label, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int l = label[i];
+    while (label[l] != l) l = label[l];
+    label[i] = l;
+}
+__global__ void cc_count_kernel(const int* __restrict__ label, int64_t n, int* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && label[i] == (int)i) atomicAdd(count, 1);
+}
+
 struct IngestWork {
     uint64_t *keys_a, *keys_b;
     int *vals_a, *tmp_a, *tmp_b, *tmp_c, *tmp_d;

@@ -213,6 +213,33 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     return 0;
 }
 
+int vb_count_components(const vb_graph* g, const int32_t* t_time, int32_t* labels, int64_t* h_count, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = g->n_c + g->n_t, E = g->n_edges;
+    if (n <= 0 || E <= 0) return VB_STATUS_BAD_ARGUMENT;
+    int* flag = labels + n;   // labels holds n + 2 ints: labels, changed flag, component count
+    iota_kernel<<<ing_grid(n), ING_THREADS, 0, st>>>(labels, n);
+    int launches = 1;
+    for (int round = 0; round < 10000; ++round) {
+        VB_CHECK(cudaMemsetAsync(flag, 0, 2 * sizeof(int), st));
+        cc_hook_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(g->t_cam, t_time, E, (int)g->n_c, labels, flag);
+        cc_jump_kernel<<<ing_grid(n), ING_THREADS, 0, st>>>(labels, n);
+        launches += 2;
+        int changed = 0;
+        VB_CHECK(cudaMemcpyAsync(&changed, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VB_CHECK(cudaStreamSynchronize(st));
+        if (!changed) break;
+    }
+    cc_count_kernel<<<ing_grid(n), ING_THREADS, 0, st>>>(labels, n, flag + 1);
+    int count = 0;
+    VB_CHECK(cudaMemcpyAsync(&count, flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VB_CHECK(cudaStreamSynchronize(st));
+    VB_KERNEL_CHECK();
+    count_launches(launches + 1);
+    *h_count = count;
+    return 0;
+}
+
 // dst[i] = src[i] + add: appends an index array of a freshly ingested chunk behind the arrays of a growing graph
 __global__ void offset_copy_kernel(int* __restrict__ dst, const int* __restrict__ src, int64_t n, int add) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -226,6 +226,16 @@ class DeviceGraph:
         g.st_ptr, g.st_idx, g.st_w = st_ptr.data_ptr(), st_idx.data_ptr(), st_w.data_ptr()
         g.sc_ptr, g.sc_idx, g.sc_w = sc_ptr.data_ptr(), sc_idx.data_ptr(), sc_w.data_ptr()
 
+    def n_components(self) -> int:
+        """Connected components of the aggregated bipartite graph (device: hooking + pointer jumping)."""
+        lib = _cabi.lib()
+        with torch.cuda.device(self.device):
+            labels = torch.empty(self.n_c + self.n_t + 2, dtype=I32, device=self.device)
+            cnt = C.c_int64(0)
+            check(lib.vb_count_components(C.byref(self.cgraph), _ptr(self.t_time), _ptr(labels), C.byref(cnt), _stream()),
+                  "vb_count_components")
+        return int(cnt.value)
+
     # ---- algorithmic bytes of one edge pass (SURVEY.md 8d: 76 B / edge + node traffic) ----
     def pass_bytes(self, kind: str) -> int:
         E, n_c, n_t = self.n_edges, self.n_c, self.n_t
