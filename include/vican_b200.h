@@ -243,11 +243,11 @@ int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair
 /* Sliced-ELL copy of the translation Laplacian for vb_trans_cg (see vb_graph).  vb_sell_count writes the slice
  * pointers (st_ptr [ceil(n_t/8)+2], sc_ptr [ceil(n_c/8)+2]) and returns the chunk totals on the host
  * (synchronises); the caller allocates 32 * chunks slots per side and vb_sell_fill fills them. */
-int64_t vb_sell_workspace_bytes(int64_t n_c, int64_t n_t);
+int64_t vb_sell_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_windows);
 int vb_sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* h_chunks_t, int64_t* h_chunks_c,
                   void* workspace, int64_t workspace_bytes, void* stream);
 int vb_sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
-                 int32_t* sc_idx, double* sc_w, void* stream);
+                 int32_t* sc_idx, double* sc_w, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t);
 /* Conjugate gradients on J^T J x = J^T t~ replaying scipy.sparse.linalg.cg as the reference
  * calls it (bipgo.py:477: x0 = 0, no preconditioner, rtol = 1e-5, atol = 0, maxiter = 10 * 3N,

@@ -90,9 +90,9 @@ SIGNATURES = {
                                  C.POINTER(VbSo3Stats), VP]),
     "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "vb_trans_cg_workspace_bytes": (I64, [I64, I64]),
-    "vb_sell_workspace_bytes": (I64, [I64, I64]),
+    "vb_sell_workspace_bytes": (I64, [I64, I64, I64]),
     "vb_sell_count": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, c_i64p, VP, I64, VP]),
-    "vb_sell_fill": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP]),
+    "vb_sell_fill": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, I64, VP]),
     "vb_trans_cg": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, F64, I64, C.c_int, VP, VP, c_i32p, VP, I64, VP, VP,
                               C.c_int, VP]),
     "vb_trans_lsqr_workspace_bytes": (I64, [I64, I64, I64]),

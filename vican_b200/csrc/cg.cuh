@@ -91,45 +91,59 @@ __global__ void sell_fill_time_kernel(const int* __restrict__ rowptr, const int*
     }
 }
 
-// camera rows: the camera-pass order keeps camera c's edges in n_win runs (window, c); their
-// concatenation is the camera's edge list in ascending time order
-__global__ void sell_fill_cam_kernel(const int* __restrict__ segptr, int64_t n_win, int64_t n_c, const int* __restrict__ c_time,
-                                     const double* __restrict__ c_w, int64_t n_slices, const int* __restrict__ ptr,
-                                     int* __restrict__ idx, double* __restrict__ w) {
+// camera rows: the camera-pass order keeps camera c's edges in n_win runs (window, c); their concatenation is
+// the camera's edge list in ascending time order.  cam_prefix[w * n_c + c] = edges of camera c in windows < w.
+__global__ void sell_cam_prefix_kernel(const int* __restrict__ segptr, int64_t n_win, int64_t n_c, int* __restrict__ prefix) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_c) return;
+    int s = 0;
+    for (int64_t w = 0; w < n_win; ++w) {
+        prefix[w * n_c + c] = s;
+        s += segptr[w * n_c + c + 1] - segptr[w * n_c + c];
+    }
+}
+
+// One warp per (slice, window): lanes (j, sub) copy run (window, camera 8 slice + j) into the row's slots
+// [prefix, prefix + run length); the warp of the last window also writes the row's padding (idx -1, w 0).
+__global__ void sell_fill_cam_kernel(const int* __restrict__ segptr, const int* __restrict__ prefix, int64_t n_win, int64_t n_c,
+                                     const int* __restrict__ c_time, const double* __restrict__ c_w, int64_t n_slices,
+                                     const int* __restrict__ ptr, int* __restrict__ idx, double* __restrict__ w) {
     const int lane = threadIdx.x & 31, j = lane >> 2, sub = lane & 3;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t slice = warp0; slice < n_slices; slice += nwarps) {
+    for (int64_t item = warp0; item < n_slices * n_win; item += nwarps) {
+        const int64_t slice = item / n_win, win = item - slice * n_win;
         const int64_t c = SELL_ROWS * slice + j;
-        const int c0 = ptr[slice], c1 = ptr[slice + 1];
-        int64_t win = 0;
-        int kbase = 0, rs = 0, re = 0;   // current run [rs, re) holds the row's elements [kbase, kbase + re - rs)
-        if (c < n_c) { rs = segptr[c]; re = segptr[c + 1]; }
-        for (int q = c0; q < c1; ++q) {
-            const int k = 4 * (q - c0) + sub;
-            bool ok = c < n_c;
-            while (ok && k >= kbase + (re - rs)) {
-                kbase += re - rs;
-                if (++win >= n_win) { ok = false; break; }
-                rs = segptr[win * n_c + c]; re = segptr[win * n_c + c + 1];
+        const int64_t c0 = ptr[slice], c1 = ptr[slice + 1];
+        if (c < n_c) {
+            const int rs = segptr[win * n_c + c], re = segptr[win * n_c + c + 1], k0 = prefix[win * n_c + c];
+            for (int i = rs + sub; i < re; i += 4) {
+                const int k = k0 + (i - rs);
+                const int64_t slot = 32 * (c0 + (k >> 2)) + 4 * j + (k & 3);
+                idx[slot] = c_time[i];
+                w[slot] = c_w[i];
             }
-            if (win >= n_win) ok = false;
-            const int64_t slot = 32 * (int64_t)q + lane;
-            const int src = rs + (k - kbase);
-            idx[slot] = ok ? c_time[src] : -1;
-            w[slot] = ok ? c_w[src] : 0.0;
+        }
+        if (win == n_win - 1) {   // padding behind the row's last element
+            int len = 0;
+            if (c < n_c) len = prefix[win * n_c + c] + segptr[win * n_c + c + 1] - segptr[win * n_c + c];
+            for (int64_t k = len + sub; k < 4 * (c1 - c0); k += 4) {
+                const int64_t slot = 32 * (c0 + (k >> 2)) + 4 * j + (k & 3);
+                idx[slot] = -1;
+                w[slot] = 0.0;
+            }
         }
     }
 }
 
 struct SellWork {
-    int *len_t, *len_c, *cnt_t, *cnt_c;
+    int *len_t, *len_c, *cnt_t, *cnt_c, *prefix;
     void* cub_tmp;
     size_t cub_bytes;
     int64_t bytes;
 };
 
-inline SellWork carve_sell(void* base, int64_t n_c, int64_t n_t) {
+inline SellWork carve_sell(void* base, int64_t n_c, int64_t n_t, int64_t n_win) {
     SellWork w;
     char* p = (char*)base;
     int64_t off = 0;
@@ -140,6 +154,7 @@ inline SellWork carve_sell(void* base, int64_t n_c, int64_t n_t) {
     };
     w.len_t = (int*)take(4 * (n_t + 1)); w.len_c = (int*)take(4 * (n_c + 1));
     w.cnt_t = (int*)take(4 * (sell_slices(n_t) + 2)); w.cnt_c = (int*)take(4 * (sell_slices(n_c) + 2));
+    w.prefix = (int*)take(4 * (n_win * n_c + 1));
     size_t b = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, (int)(sell_slices(n_t > n_c ? n_t : n_c) + 2));
     w.cub_bytes = b + 256;
@@ -151,7 +166,7 @@ inline SellWork carve_sell(void* base, int64_t n_c, int64_t n_t) {
 inline int sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* h_chunks_t, int64_t* h_chunks_c,
                       void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     const int64_t n_c = g->n_c, n_t = g->n_t;
-    SellWork w = carve_sell(workspace, n_c, n_t);
+    SellWork w = carve_sell(workspace, n_c, n_t, g->n_windows);
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     const int64_t ns_t = sell_slices(n_t), ns_c = sell_slices(n_c);
     int tot_t = 0, tot_c = 0;
@@ -178,8 +193,10 @@ inline int sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64
 }
 
 inline int sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
-                     int32_t* sc_idx, double* sc_w, cudaStream_t st) {
+                     int32_t* sc_idx, double* sc_w, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     const int64_t n_c = g->n_c, n_t = g->n_t;
+    SellWork w = carve_sell(workspace, n_c, n_t, g->n_windows);
+    if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     const int64_t ns_t = sell_slices(n_t), ns_c = sell_slices(n_c);
     const int cap = sm_count() * 8;
     if (ns_t > 0) {
@@ -187,11 +204,13 @@ inline int sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, 
         sell_fill_time_kernel<<<grid < cap ? grid : cap, CG_THREADS, 0, st>>>(g->t_rowptr, g->t_cam, g->t_w, n_t, ns_t, st_ptr, st_idx, st_w);
     }
     {
-        int grid = (int)((ns_c + CG_WARPS - 1) / CG_WARPS);
-        sell_fill_cam_kernel<<<grid < cap ? grid : cap, CG_THREADS, 0, st>>>(g->c_segptr, g->n_windows, n_c, g->c_time, g->c_w, ns_c, sc_ptr, sc_idx, sc_w);
+        sell_cam_prefix_kernel<<<(int)((n_c + 255) / 256), 256, 0, st>>>(g->c_segptr, g->n_windows, n_c, w.prefix);
+        const int64_t items = ns_c * g->n_windows;
+        int grid = (int)((items + CG_WARPS - 1) / CG_WARPS);
+        sell_fill_cam_kernel<<<grid < cap ? grid : cap, CG_THREADS, 0, st>>>(g->c_segptr, w.prefix, g->n_windows, n_c, g->c_time, g->c_w, ns_c, sc_ptr, sc_idx, sc_w);
     }
     VB_KERNEL_CHECK();
-    count_launches(ns_t > 0 ? 2 : 1);
+    count_launches(ns_t > 0 ? 3 : 2);
     return 0;
 }
 

@@ -333,7 +333,7 @@ int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair
 
 int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_cg(nullptr, n_c, n_t).bytes; }
 
-int64_t vb_sell_workspace_bytes(int64_t n_c, int64_t n_t) { return carve_sell(nullptr, n_c, n_t).bytes; }
+int64_t vb_sell_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_windows) { return carve_sell(nullptr, n_c, n_t, n_windows).bytes; }
 
 int vb_sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* h_chunks_t, int64_t* h_chunks_c,
                   void* workspace, int64_t workspace_bytes, void* stream) {
@@ -341,8 +341,8 @@ int vb_sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* 
 }
 
 int vb_sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
-                 int32_t* sc_idx, double* sc_w, void* stream) {
-    return sell_fill(g, st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w, (cudaStream_t)stream);
+                 int32_t* sc_idx, double* sc_w, void* workspace, int64_t workspace_bytes, void* stream) {
+    return sell_fill(g, st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t, double rtol,

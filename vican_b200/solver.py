@@ -209,7 +209,7 @@ class DeviceGraph:
             ns_t, ns_c = (self.n_t + 7) // 8, (self.n_c + 7) // 8
             st_ptr = torch.empty(ns_t + 2, dtype=I32, device=dev)
             sc_ptr = torch.empty(ns_c + 2, dtype=I32, device=dev)
-            wsb = int(lib.vb_sell_workspace_bytes(self.n_c, self.n_t))
+            wsb = int(lib.vb_sell_workspace_bytes(self.n_c, self.n_t, self.n_windows))
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             ct, cc = C.c_int64(0), C.c_int64(0)
             check(lib.vb_sell_count(C.byref(self.cgraph), _ptr(st_ptr), _ptr(sc_ptr), C.byref(ct), C.byref(cc),
@@ -219,7 +219,7 @@ class DeviceGraph:
             sc_idx = torch.empty(32 * max(int(cc.value), 1), dtype=I32, device=dev)
             sc_w = torch.empty(32 * max(int(cc.value), 1), dtype=F64, device=dev)
             check(lib.vb_sell_fill(C.byref(self.cgraph), _ptr(st_ptr), _ptr(st_idx), _ptr(st_w), _ptr(sc_ptr),
-                                   _ptr(sc_idx), _ptr(sc_w), _stream()), "vb_sell_fill")
+                                   _ptr(sc_idx), _ptr(sc_w), _ptr(ws), wsb, _stream()), "vb_sell_fill")
         self._sell = (st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w)
         self.sell_chunks = (int(ct.value), int(cc.value))
         g = self.cgraph
