@@ -173,30 +173,43 @@ __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const doubl
 }
 
 // bipgo.py:323-332 (+ Wt = Lambda_T Y_t, the time half of the next L-apply).  Yt12 / Wt12 use the
-// padded gather layout (3 rows x 4 doubles) and may alias.
+// padded gather layout (3 rows x 4 doubles) and may alias.  One thread per node; the padded rows move as
+// 256-bit loads / stores and the two compact outputs (r_t, Lambda_T: 72-byte records) leave through a
+// shared-memory transpose so that the CTA writes them as contiguous, coalesced streams.
+__device__ __forceinline__ void st_row256(double* p, double a, double b, double c) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(0.0) : "memory");
+}
+__device__ __forceinline__ void ld_row256_plain(const double* p, double& a, double& b, double& c) {
+    double pad;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(pad) : "l"(p));
+    (void)pad;
+}
 __global__ void __launch_bounds__(NODE_THREADS) dual_update_kernel(const double* Yt12, double* __restrict__ r_t, double* __restrict__ lamT, double* Wt12,
                                    int64_t n_t) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_t) return;
-    double y[9], rot[9], si[9], w[9];
+    __shared__ double sR[NODE_THREADS * 9], sL[NODE_THREADS * 9];
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t t = t0 + threadIdx.x;
+    if (t < n_t) {
+        double y[9], rot[9], si[9], w[9];
+        ld_row256_plain(Yt12 + GSTRIDE * t, y[0], y[1], y[2]);
+        ld_row256_plain(Yt12 + GSTRIDE * t + 4, y[3], y[4], y[5]);
+        ld_row256_plain(Yt12 + GSTRIDE * t + 8, y[6], y[7], y[8]);
+        node_factors(y, rot, nullptr, si);
+        mm3(si, y, w);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) y[3 * i + j] = Yt12[GSTRIDE * t + 4 * i + j];
-    node_factors(y, rot, nullptr, si);
-    mm3(si, y, w);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        r_t[9 * t + i] = rot[i];
-        lamT[9 * t + i] = si[i];
-    }
-    if (Wt12) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) Wt12[GSTRIDE * t + 4 * i + j] = w[3 * i + j];
-            Wt12[GSTRIDE * t + 4 * i + 3] = 0.0;
+        for (int i = 0; i < 9; ++i) { sR[9 * threadIdx.x + i] = rot[i]; sL[9 * threadIdx.x + i] = si[i]; }
+        if (Wt12) {
+            st_row256(Wt12 + GSTRIDE * t, w[0], w[1], w[2]);
+            st_row256(Wt12 + GSTRIDE * t + 4, w[3], w[4], w[5]);
+            st_row256(Wt12 + GSTRIDE * t + 8, w[6], w[7], w[8]);
         }
+    }
+    __syncthreads();
+    const int64_t n_here = (n_t - t0) < NODE_THREADS ? (n_t - t0) : NODE_THREADS;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const int i = q * NODE_THREADS + threadIdx.x;
+        if (i < 9 * n_here) { r_t[9 * t0 + i] = sR[i]; lamT[9 * t0 + i] = sL[i]; }
     }
 }
 
