@@ -447,7 +447,8 @@ struct CgMv {
 
 constexpr int CG_MV_THREADS = 128;
 constexpr int CG_MV_WARPS = CG_MV_THREADS / 32;
-constexpr int CG_U = 8;               // chunks (of 32 slots) per pipeline step of a warp
+constexpr int CG_U = 4;               // chunks (of 32 slots) per pipeline step of a warp
+constexpr int CG_MV_CTAS = 4;         // resident CTAs per SM the register budget is set for
 
 __device__ __forceinline__ int ld_stream_i(const int* p) {
     int v;
@@ -460,34 +461,32 @@ __device__ __forceinline__ double ld_stream_d(const double* p) {
     return v;
 }
 
-// A warp streams the contiguous chunk range of its slices [s0, s1) through a three-stage software pipeline
-//   A: (index, weight) of step s+2, coalesced        B: 256-bit row gathers of step s+1
-//   C: products of step s -> shared memory, then lanes (j, d < 3) advance the 8 x 3 sequential chains
-// so the only serial work left per element is the chain's own DADD.  Slice boundaries inside a step are
-// handled in the chain loop (rows finish, the next slice's rows start).
+// A warp streams the contiguous chunk range of its slices [s0, s1).  Lane (j, d) owns the chain of coordinate d
+// of row j of the current slice and does everything for it itself: it reads its row's four (index, weight)
+// pairs of a chunk with one 128-bit and one 256-bit load (the three lanes of a row read the same addresses:
+// one request), gathers component d of the four far-endpoint rows (the three lanes of a row hit one 32-byte
+// sector), and advances the chain in registers -- no shared memory, no cross-lane traffic.  Two-stage software
+// pipeline: (index, weight) of step s+1 are in flight while step s is gathered and chained; the other warps of
+// the SM cover the gather latency.  L1 wavefronts per chunk: 32 (gathers) + 3, the floor for this access pattern.
+// Slice boundaries inside a step are handled in the chain loop (rows finish, the next slice's rows start).
 template <bool DIAGMODE>
-__device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, int64_t s1, double* pw, bool count_pq, double& pq) {
+__device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, int64_t s1, bool count_pq, double& pq) {
     if (s0 >= s1) return;
     const int lane = threadIdx.x & 31, j = lane >> 2, d = lane & 3;
     const int cbeg = __ldg(S.ptr + s0), cend = __ldg(S.ptr + s1);
-    int idx_nx[CG_U]; double w_nx[CG_U];
-    double g[CG_U][3], w_cur[CG_U];
+    int4 idx_nx[CG_U]; double w_nx[CG_U][4];
     auto loadA = [&](int q0) {
 #pragma unroll
         for (int u = 0; u < CG_U; ++u) {
-            idx_nx[u] = -1; w_nx[u] = 0.0;
+            idx_nx[u] = make_int4(-1, -1, -1, -1);
+            w_nx[u][0] = w_nx[u][1] = w_nx[u][2] = w_nx[u][3] = 0.0;
             if (q0 + u < cend) {
-                const int64_t slot = 32 * (int64_t)(q0 + u) + lane;
-                idx_nx[u] = ld_stream_i(S.idx + slot); w_nx[u] = ld_stream_d(S.w + slot);
+                const int64_t base = 32 * (int64_t)(q0 + u) + 4 * j;
+                asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(idx_nx[u].x), "=r"(idx_nx[u].y), "=r"(idx_nx[u].z), "=r"(idx_nx[u].w) : "l"(S.idx + base));
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                             : "=d"(w_nx[u][0]), "=d"(w_nx[u][1]), "=d"(w_nx[u][2]), "=d"(w_nx[u][3]) : "l"(S.w + base));
             }
-        }
-    };
-    auto issueB = [&]() {
-#pragma unroll
-        for (int u = 0; u < CG_U; ++u) {
-            w_cur[u] = w_nx[u];
-            g[u][0] = g[u][1] = g[u][2] = DIAGMODE ? 1.0 : 0.0;
-            if (!DIAGMODE && idx_nx[u] >= 0) ld_row256(S.p_other + 4 * (int64_t)idx_nx[u], g[u][0], g[u][1], g[u][2]);
         }
     };
     // chain state of the current slice (+ the next slice's row constants, fetched one slice ahead)
@@ -524,17 +523,27 @@ __device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, in
     fetch_row(s0);
     start_row(s0);
     loadA(cbeg);
-    issueB();
-    loadA(cbeg + CG_U);
+    const int dd = d < 3 ? d : 0;
+    const uint64_t keep = policy_evict_last();   // the gathered vectors are re-read by many rows
     for (int q0 = cbeg; q0 < cend; q0 += CG_U) {
+        // gathers of this step (component d of the four far-endpoint rows of every chunk), then the next step's
+        // (index, weight) stream; the products are rounded before they are added (scipy: no FMA)
+        double pr[CG_U][4];
 #pragma unroll
         for (int u = 0; u < CG_U; ++u) {
-            double* o = pw + (u * 32 + lane) * 3;
-            o[0] = __dmul_rn(w_cur[u], g[u][0]); o[1] = __dmul_rn(w_cur[u], g[u][1]); o[2] = __dmul_rn(w_cur[u], g[u][2]);
+            const int id[4] = {idx_nx[u].x, idx_nx[u].y, idx_nx[u].z, idx_nx[u].w};
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {
+                double pv = DIAGMODE ? 1.0 : 0.0;
+                if (!DIAGMODE && id[sub] >= 0) pv = ld_keep(S.p_other + 4 * (int64_t)id[sub] + dd, keep);
+                pr[u][sub] = pv;
+            }
         }
-        issueB();                  // gathers of the next step (their indices arrived one step ago)
-        loadA(q0 + 2 * CG_U);
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < CG_U; ++u)
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) pr[u][sub] = __dmul_rn(w_nx[u][sub], pr[u][sub]);
+        loadA(q0 + CG_U);
 #pragma unroll
         for (int u = 0; u < CG_U; ++u) {
             const int c = q0 + u;
@@ -545,22 +554,20 @@ __device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, in
                     slice_end = __ldg(S.ptr + slice + 1);
                     start_row(slice);
                 }
-                const double* pb = pw + (u * 32 + 4 * j) * 3 + (d < 3 ? d : 0);   // lanes d == 3 carry no chain
                 if (pending && ins < k + 4) {
 #pragma unroll
                     for (int sub = 0; sub < 4; ++sub) {
                         if (pending && k == ins) { acc = __dadd_rn(acc, diag); pending = false; }
-                        acc = DIAGMODE ? __dadd_rn(acc, pb[3 * sub]) : __dsub_rn(acc, pb[3 * sub]);
+                        acc = DIAGMODE ? __dadd_rn(acc, pr[u][sub]) : __dsub_rn(acc, pr[u][sub]);
                         ++k;
                     }
                 } else {
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) acc = DIAGMODE ? __dadd_rn(acc, pb[3 * sub]) : __dsub_rn(acc, pb[3 * sub]);
+                    for (int sub = 0; sub < 4; ++sub) acc = DIAGMODE ? __dadd_rn(acc, pr[u][sub]) : __dsub_rn(acc, pr[u][sub]);
                     k += 4;
                 }
             }
         }
-        __syncwarp();
     }
     // the last slice with chunks, and any trailing slices without (rows with no local edges)
     for (;;) {
@@ -572,27 +579,25 @@ __device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, in
 
 // q = (J^T J) p in scipy's CSR row order, or (DIAGMODE) the weighted degrees by the same sequential sums
 template <bool DIAGMODE>
-__global__ void __launch_bounds__(CG_MV_THREADS, 4) cg_matvec_kernel(CgMv a) {
+__global__ void __launch_bounds__(CG_MV_THREADS, CG_MV_CTAS) cg_matvec_kernel(CgMv a) {
     if (!DIAGMODE && a.sc[CG_DONE] != 0.0) return;
-    __shared__ __align__(16) double prod[CG_MV_WARPS * CG_U * 32 * 3];
     const int wv = threadIdx.x >> 5;
-    double* pw = prod + wv * (CG_U * 32 * 3);
     const int64_t gw = (int64_t)blockIdx.x * CG_MV_WARPS + wv;
     const int64_t nw = (int64_t)gridDim.x * CG_MV_WARPS;
     double pq = 0.0;
     if (gw < a.warps_cam) {
         const int64_t per = (a.cam.n_slices + a.warps_cam - 1) / a.warps_cam;
         const int64_t s0 = gw * per, s1 = (s0 + per < a.cam.n_slices) ? s0 + per : a.cam.n_slices;
-        cg_stream_rows<DIAGMODE>(a.cam, s0, s1, pw, !a.multi, pq);
+        cg_stream_rows<DIAGMODE>(a.cam, s0, s1, !a.multi, pq);
     } else {
         const int64_t wt = nw - a.warps_cam, me = gw - a.warps_cam;
         const int64_t per = (a.time.n_slices + wt - 1) / (wt > 0 ? wt : 1);
         const int64_t s0 = me * per, s1 = (s0 + per < a.time.n_slices) ? s0 + per : a.time.n_slices;
-        cg_stream_rows<DIAGMODE>(a.time, s0, s1, pw, true, pq);
+        cg_stream_rows<DIAGMODE>(a.time, s0, s1, true, pq);
     }
     if (DIAGMODE) return;
-    // p . q: camera warps own whole CTAs [0, ceil(warps_cam / 4)) when warps_cam is a multiple of 4 (the host
-    // rounds it), so the two parts can be summed separately and in a fixed order
+    // p . q: camera warps own whole CTAs [0, warps_cam / 4) (the host rounds warps_cam to CTAs), so the two parts
+    // are summed separately and in a fixed order
     const double v[1] = {pq};
     if (cg_block_partial<1, CG_MV_WARPS>(v, a.tab, a.ticket)) {
         const int nb_cam = a.warps_cam / CG_MV_WARPS;
