@@ -162,8 +162,9 @@ int64_t vb_ingest_workspace_bytes(int64_t n_raw);
  * [n_raw] (sorted position -> raw index), raw_pair [n_raw] (pair id per sorted position) and
  * returns the number of pairs in *h_n_pairs (host; synchronises the stream). */
 int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64_t n_c, int64_t n_t,
-                   int32_t* raw_perm, int32_t* raw_pair, int64_t* h_n_pairs, void* workspace,
-                   int64_t workspace_bytes, void* stream);
+                   int32_t* raw_perm, int32_t* raw_pair, int64_t* h_n_pairs,
+                   int32_t* h_sorted /* out, may be NULL: 1 if the detections arrived ordered by (time, camera) */,
+                   void* workspace, int64_t workspace_bytes, void* stream);
 /* step 2: fold + aggregate into the time-sorted arrays, build the camera-pass copy, row
  * pointers, degrees and camera tiles.  pair_start [E+1] indexes the sorted raw list.  The
  * camera-pass arrays c_B / c_time / c_w are ordered by (time window, camera, time): c_order [E]
@@ -175,6 +176,16 @@ int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64
  * PADDING: t_B / c_B must be allocated for E + 2 blocks and t_cam / c_time for E + 8 indices
  * (the edge passes stream them with 16-byte granular bulk copies).
  * WORKSPACE of vb_ingest_build: vb_ingest_workspace_bytes(max(n_raw, vb_ingest_windows(...) * n_c + 1)). */
+/* Optional arrival schedule of the rotation array R of vb_ingest_build (host-to-device copy still in flight on
+ * another stream): chunk k holds the detections [h_raw_end[k-1], h_raw_end[k]) and is complete when the CUDA event
+ * h_events[k] (cudaEvent_t) has fired.  With sorted_input (vb_ingest_sort's h_sorted) every chunk is folded as soon as
+ * it has landed, under the copy of the next one; otherwise the fold waits for all events.  n_chunks <= 64. */
+typedef struct vb_arrival {
+    int32_t n_chunks;
+    int32_t sorted_input;
+    const int64_t* h_raw_end;   /* [n_chunks] host */
+    void* const*   h_events;    /* [n_chunks] host array of cudaEvent_t */
+} vb_arrival;
 int64_t vb_ingest_max_tiles(int64_t n_edges, int64_t n_c, int64_t tile_len);
 int64_t vb_ingest_windows(int64_t n_edges, int64_t n_c, int64_t tile_len);
 int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* marker, const double* R,
@@ -184,7 +195,8 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
                     int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
                     int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_off,
-                    int64_t* h_n_tiles, double* deg_t, double* deg_c, void* workspace,
+                    int64_t* h_n_tiles, double* deg_t, double* deg_c,
+                    const vb_arrival* arrival /* NULL: R is resident */, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
 /* Number of connected components of the bipartite graph of aggregated edges (min-label hooking + pointer
@@ -247,7 +259,8 @@ int64_t vb_sell_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_windows);
 int vb_sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* h_chunks_t, int64_t* h_chunks_c,
                   void* workspace, int64_t workspace_bytes, void* stream);
 int vb_sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
-                 int32_t* sc_idx, double* sc_w, void* workspace, int64_t workspace_bytes, void* stream);
+                 int32_t* sc_idx, double* sc_w, int64_t chunks_c /* as returned by vb_sell_count */, void* workspace,
+                 int64_t workspace_bytes, void* stream);
 int64_t vb_trans_cg_workspace_bytes(int64_t n_c, int64_t n_t);
 /* Conjugate gradients on J^T J x = J^T t~ replaying scipy.sparse.linalg.cg as the reference
  * calls it (bipgo.py:477: x0 = 0, no preconditioner, rtol = 1e-5, atol = 0, maxiter = 10 * 3N,

@@ -39,6 +39,10 @@ class VbGraph(C.Structure):
     ]
 
 
+class VbArrival(C.Structure):
+    _fields_ = [("n_chunks", I32), ("sorted_input", I32), ("h_raw_end", c_i64p), ("h_events", C.POINTER(VP))]
+
+
 class VbSo3Options(C.Structure):
     _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP),
                 ("profile_events", I32), ("no_shortcut", I32), ("identity_start", I32), ("eval_gap", I32),
@@ -69,12 +73,12 @@ SIGNATURES = {
     "vb_distance_so3_batch": (C.c_int, [VP, VP, VP, I64, VP]),
     "vb_se3_left_compose_batch": (C.c_int, [VP, VP, VP, VP, VP, VP, I64, C.c_int, VP]),
     "vb_ingest_workspace_bytes": (I64, [I64]),
-    "vb_ingest_sort": (C.c_int, [VP, VP, I64, I64, I64, VP, VP, c_i64p, VP, I64, VP]),
+    "vb_ingest_sort": (C.c_int, [VP, VP, I64, I64, I64, VP, VP, c_i64p, c_i32p, VP, I64, VP]),
     "vb_ingest_max_tiles": (I64, [I64, I64, I64]),
     "vb_ingest_windows": (I64, [I64, I64, I64]),
     "vb_ingest_build": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, I64, C.c_int, VP, VP, I64, I64, I64, I64,
                                   VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, c_i64p, VP, VP,
-                                  VP, I64, VP]),
+                                  C.POINTER(VbArrival), VP, I64, VP]),
     "vb_count_components": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, VP]),
     "vb_offset_copy_i32": (C.c_int, [VP, VP, I64, I32, VP]),
     "vb_add_inplace_f64": (C.c_int, [VP, VP, I64, VP]),
@@ -92,7 +96,7 @@ SIGNATURES = {
     "vb_trans_cg_workspace_bytes": (I64, [I64, I64]),
     "vb_sell_workspace_bytes": (I64, [I64, I64, I64]),
     "vb_sell_count": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, c_i64p, VP, I64, VP]),
-    "vb_sell_fill": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, I64, VP]),
+    "vb_sell_fill": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, I64, VP, I64, VP]),
     "vb_trans_cg": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, F64, I64, C.c_int, VP, VP, c_i32p, VP, I64, VP, VP,
                               C.c_int, VP]),
     "vb_trans_lsqr_workspace_bytes": (I64, [I64, I64, I64]),

@@ -103,37 +103,56 @@ __global__ void sell_cam_prefix_kernel(const int* __restrict__ segptr, int64_t n
     }
 }
 
-// One warp per (slice, window): lanes (j, sub) copy run (window, camera 8 slice + j) into the row's slots
-// [prefix, prefix + run length); the warp of the last window also writes the row's padding (idx -1, w 0).
+// One warp per (slice, range of SELL_FILL_CHUNKS chunks): lane (j, sub) locates element k = 4 q + sub of row
+// 8 slice + j in the row's runs (binary search in the prefix table at the start of the range, then a monotone
+// walk) and the warp writes whole chunks (coalesced 128 / 256-byte stores); padding: idx -1, w 0.
+constexpr int SELL_FILL_CHUNKS = 64;
 __global__ void sell_fill_cam_kernel(const int* __restrict__ segptr, const int* __restrict__ prefix, int64_t n_win, int64_t n_c,
                                      const int* __restrict__ c_time, const double* __restrict__ c_w, int64_t n_slices,
-                                     const int* __restrict__ ptr, int* __restrict__ idx, double* __restrict__ w) {
+                                     const int* __restrict__ ptr, const int* __restrict__ item_ptr, int64_t n_items,
+                                     int* __restrict__ idx, double* __restrict__ w) {
     const int lane = threadIdx.x & 31, j = lane >> 2, sub = lane & 3;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t item = warp0; item < n_slices * n_win; item += nwarps) {
-        const int64_t slice = item / n_win, win = item - slice * n_win;
+    for (int64_t item = warp0; item < n_items; item += nwarps) {
+        // slice of this item: item_ptr[s] = first item of slice s (ascending): binary search
+        int64_t lo = 0, hi = n_slices;
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (item_ptr[mid] <= item) lo = mid; else hi = mid; }
+        const int64_t slice = lo;
+        const int c0 = ptr[slice], c1 = ptr[slice + 1];
+        const int qa = (int)(item - item_ptr[slice]) * SELL_FILL_CHUNKS;
+        const int qb = (qa + SELL_FILL_CHUNKS < c1 - c0) ? qa + SELL_FILL_CHUNKS : c1 - c0;
         const int64_t c = SELL_ROWS * slice + j;
-        const int64_t c0 = ptr[slice], c1 = ptr[slice + 1];
-        if (c < n_c) {
-            const int rs = segptr[win * n_c + c], re = segptr[win * n_c + c + 1], k0 = prefix[win * n_c + c];
-            for (int i = rs + sub; i < re; i += 4) {
-                const int k = k0 + (i - rs);
-                const int64_t slot = 32 * (c0 + (k >> 2)) + 4 * j + (k & 3);
-                idx[slot] = c_time[i];
-                w[slot] = c_w[i];
-            }
+        // window holding element 4 qa + sub of camera c
+        int64_t win = 0;
+        int kbase = 0, rs = 0, re = 0;
+        bool ok = c < n_c;
+        if (ok) {
+            const int k = 4 * qa + sub;
+            int64_t a = 0, b2 = n_win;
+            while (b2 - a > 1) { const int64_t mid = (a + b2) >> 1; if (prefix[mid * n_c + c] <= k) a = mid; else b2 = mid; }
+            win = a; kbase = prefix[win * n_c + c]; rs = segptr[win * n_c + c]; re = segptr[win * n_c + c + 1];
         }
-        if (win == n_win - 1) {   // padding behind the row's last element
-            int len = 0;
-            if (c < n_c) len = prefix[win * n_c + c] + segptr[win * n_c + c + 1] - segptr[win * n_c + c];
-            for (int64_t k = len + sub; k < 4 * (c1 - c0); k += 4) {
-                const int64_t slot = 32 * (c0 + (k >> 2)) + 4 * j + (k & 3);
-                idx[slot] = -1;
-                w[slot] = 0.0;
+        for (int q = qa; q < qb; ++q) {
+            const int k = 4 * q + sub;
+            while (ok && k >= kbase + (re - rs)) {
+                kbase += re - rs;
+                if (++win >= n_win) { ok = false; break; }
+                rs = segptr[win * n_c + c]; re = segptr[win * n_c + c + 1];
             }
+            const int64_t slot = 32 * (int64_t)(c0 + q) + lane;
+            const int src = rs + (k - kbase);
+            idx[slot] = ok ? c_time[src] : -1;
+            w[slot] = ok ? c_w[src] : 0.0;
         }
     }
+}
+
+// items per slice (ceil(chunks / SELL_FILL_CHUNKS)); entry n_slices is the scan's sentinel
+__global__ void sell_items_kernel(const int* __restrict__ ptr, int64_t n_slices, int* __restrict__ cnt) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_slices) return;
+    cnt[s] = s < n_slices ? (ptr[s + 1] - ptr[s] + SELL_FILL_CHUNKS - 1) / SELL_FILL_CHUNKS : 0;
 }
 
 struct SellWork {
@@ -193,7 +212,7 @@ inline int sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64
 }
 
 inline int sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
-                     int32_t* sc_idx, double* sc_w, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                     int32_t* sc_idx, double* sc_w, int64_t chunks_c, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
     const int64_t n_c = g->n_c, n_t = g->n_t;
     SellWork w = carve_sell(workspace, n_c, n_t, g->n_windows);
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
@@ -205,12 +224,17 @@ inline int sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, 
     }
     {
         sell_cam_prefix_kernel<<<(int)((n_c + 255) / 256), 256, 0, st>>>(g->c_segptr, g->n_windows, n_c, w.prefix);
-        const int64_t items = ns_c * g->n_windows;
-        int grid = (int)((items + CG_WARPS - 1) / CG_WARPS);
-        sell_fill_cam_kernel<<<grid < cap ? grid : cap, CG_THREADS, 0, st>>>(g->c_segptr, w.prefix, g->n_windows, n_c, g->c_time, g->c_w, ns_c, sc_ptr, sc_idx, sc_w);
+        sell_items_kernel<<<(int)((ns_c + 256) / 256), 256, 0, st>>>(sc_ptr, ns_c, w.cnt_c);
+        size_t tb = w.cub_bytes;
+        VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.cnt_c, w.len_c, (int)(ns_c + 1), st));
+        // upper bound of the item count without a read-back: every slice has < chunks / 64 + 1 items
+        const int64_t items_max = chunks_c / SELL_FILL_CHUNKS + ns_c;
+        int grid = (int)((items_max + CG_WARPS - 1) / CG_WARPS);
+        sell_fill_cam_kernel<<<grid < cap ? grid : cap, CG_THREADS, 0, st>>>(g->c_segptr, w.prefix, g->n_windows, n_c, g->c_time, g->c_w, ns_c,
+                                                                             sc_ptr, w.len_c, items_max, sc_idx, sc_w);
     }
     VB_KERNEL_CHECK();
-    count_launches(ns_t > 0 ? 3 : 2);
+    count_launches(ns_t > 0 ? 4 : 3);
     return 0;
 }
 

@@ -26,6 +26,15 @@ struct HeadFlagKey {
     __host__ __device__ int operator()(int i) const { return (i > 0 && keys[i] != keys[i - 1]) ? 1 : 0; }
 };
 
+// pair id one past the last pair that lies completely inside the first raw_end[k] sorted detections
+__global__ void chunk_pairs_kernel(const int* __restrict__ raw_pair, const int64_t* __restrict__ raw_end, int n_chunks, int64_t n_raw,
+                                   int64_t n_pairs, int64_t* __restrict__ pair_end) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_chunks) return;
+    const int64_t e = raw_end[k];
+    pair_end[k] = e >= n_raw ? n_pairs : (int64_t)raw_pair[e];   // the pair of detection e may straddle the boundary: excluded
+}
+
 __global__ void check_sorted_ct_kernel(const int* __restrict__ time, const int* __restrict__ cam, int64_t n, int* __restrict__ unsorted_flag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
@@ -143,14 +152,14 @@ constexpr int FOLD_THREADS = 256;
 __global__ void __launch_bounds__(FOLD_THREADS)
 fold_both_kernel(const int* __restrict__ marker, const double* __restrict__ R, const double* __restrict__ k_r,
                  const double* __restrict__ k_t, const double* __restrict__ markerC, int round_f32,
-                 const int* __restrict__ raw_perm, const int* __restrict__ pair_start, int64_t n_pairs,
+                 const int* __restrict__ raw_perm, const int* __restrict__ pair_start, int64_t p_begin, int64_t n_pairs,
                  const int* __restrict__ t_time, const int* __restrict__ c_pos, double* __restrict__ t_B,
                  double* __restrict__ t_a, double* __restrict__ t_w, double* __restrict__ c_B, int* __restrict__ c_time,
                  double* __restrict__ c_w) {
     __shared__ double sB[FOLD_THREADS * 9];
     __shared__ double sW[FOLD_THREADS];
     __shared__ int sPos[FOLD_THREADS], sTime[FOLD_THREADS];
-    const int64_t p0 = (int64_t)blockIdx.x * FOLD_THREADS;
+    const int64_t p0 = p_begin + (int64_t)blockIdx.x * FOLD_THREADS;   // pairs [p_begin, n_pairs) of this launch
     const int64_t p = p0 + threadIdx.x;
     if (p < n_pairs) {
         const int s = pair_start[p], e = pair_start[p + 1];
@@ -376,7 +385,8 @@ inline IngestWork carve_ingest(void* base, int64_t n) {
 }
 
 inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n_c, int64_t n_t, int* raw_perm,
-                       int* raw_pair, int64_t* h_n_pairs, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                       int* raw_pair, int64_t* h_n_pairs, int32_t* h_sorted, void* workspace, int64_t workspace_bytes,
+                       cudaStream_t st) {
     if (n_raw <= 0) return VB_STATUS_BAD_ARGUMENT;
     IngestWork w = carve_ingest(workspace, n_raw);
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
@@ -406,6 +416,7 @@ inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n
     VB_CHECK(cudaMemcpyAsync(&last, raw_pair + (n_raw - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CHECK(cudaStreamSynchronize(st));
     *h_n_pairs = (int64_t)last + 1;
+    if (h_sorted) *h_sorted = unsorted ? 0 : 1;
     count_launches(unsorted ? 2 : 2);   // check_sorted + (make_keys | iota); CUB's sort / scan are library kernels
     return 0;
 }

@@ -154,8 +154,9 @@ int64_t vb_ingest_workspace_bytes(int64_t n_raw) {
 }
 
 int vb_ingest_sort(const int32_t* cam, const int32_t* time, int64_t n_raw, int64_t n_c, int64_t n_t, int32_t* raw_perm,
-                   int32_t* raw_pair, int64_t* h_n_pairs, void* workspace, int64_t workspace_bytes, void* stream) {
-    return ingest_sort(cam, time, n_raw, n_c, n_t, raw_perm, raw_pair, h_n_pairs, workspace, workspace_bytes,
+                   int32_t* raw_pair, int64_t* h_n_pairs, int32_t* h_sorted, void* workspace, int64_t workspace_bytes,
+                   void* stream) {
+    return ingest_sort(cam, time, n_raw, n_c, n_t, raw_perm, raw_pair, h_n_pairs, h_sorted, workspace, workspace_bytes,
                        (cudaStream_t)stream);
 }
 
@@ -171,9 +172,10 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
                     int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
                     int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_off, int64_t* h_n_tiles, double* deg_t,
-                    double* deg_c, void* workspace, int64_t workspace_bytes, void* stream) {
+                    double* deg_c, const vb_arrival* arrival, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_raw <= 0 || n_pairs <= 0 || tile_len <= 0) return VB_STATUS_BAD_ARGUMENT;
+    if (arrival != nullptr && (arrival->n_chunks < 1 || arrival->n_chunks > 64)) return VB_STATUS_BAD_ARGUMENT;
     const int64_t E = n_pairs;
     const int64_t n_seg_ws = ingest_windows(E, n_c, tile_len) * n_c + 1;   // a chunk can hold fewer detections than cameras
     IngestWork w = carve_ingest(workspace, n_raw > n_seg_ws ? n_raw : n_seg_ws);
@@ -193,8 +195,33 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                                              c_order, (int)E, 0, key_bits(n_c, n_win), st));
     seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>((const int*)keys32_b, nullptr, c_segptr, E, n_seg);
     inverse_perm_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(c_order, c_pos, E);
-    fold_both_kernel<<<(int)((E + FOLD_THREADS - 1) / FOLD_THREADS), FOLD_THREADS, 0, st>>>(
-        marker, R, k_r, k_t, markerC, round_kr_f32, raw_perm, pair_start, E, t_time, c_pos, t_B, t_a, t_w, c_B, c_time, c_w);
+    // The fold is the only step that reads the rotations (72 of the 92 bytes per detection).  When they are still
+    // crossing PCIe (vb_arrival: chunks of consecutive detections, one event each) and the detections arrived sorted
+    // (sorted position = raw index), every chunk is folded as soon as it has landed, under the copy of the next.
+    int64_t h_pair_end[64];
+    int n_fold = 1;
+    h_pair_end[0] = E;
+    if (arrival != nullptr && arrival->sorted_input && arrival->n_chunks > 1) {
+        n_fold = arrival->n_chunks;
+        int64_t* d_tmp = (int64_t*)w.keys_a;   // keys_a is free again (the sort has consumed it)
+        VB_CHECK(cudaMemcpyAsync(d_tmp, arrival->h_raw_end, n_fold * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        chunk_pairs_kernel<<<1, 64, 0, st>>>(raw_pair, d_tmp, n_fold, n_raw, E, d_tmp + 64);
+        VB_CHECK(cudaMemcpyAsync(h_pair_end, d_tmp + 64, n_fold * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        VB_CHECK(cudaStreamSynchronize(st));
+        h_pair_end[n_fold - 1] = E;
+    }
+    int64_t p_lo = 0;
+    for (int kf = 0; kf < n_fold; ++kf) {
+        if (arrival != nullptr) {
+            if (n_fold > 1) VB_CHECK(cudaStreamWaitEvent(st, (cudaEvent_t)arrival->h_events[kf], 0));
+            else for (int q = 0; q < arrival->n_chunks; ++q) VB_CHECK(cudaStreamWaitEvent(st, (cudaEvent_t)arrival->h_events[q], 0));
+        }
+        const int64_t p_hi = h_pair_end[kf];
+        if (p_hi > p_lo)
+            fold_both_kernel<<<(int)((p_hi - p_lo + FOLD_THREADS - 1) / FOLD_THREADS), FOLD_THREADS, 0, st>>>(
+                marker, R, k_r, k_t, markerC, round_kr_f32, raw_perm, pair_start, p_lo, p_hi, t_time, c_pos, t_B, t_a, t_w, c_B, c_time, c_w);
+        p_lo = p_hi > p_lo ? p_hi : p_lo;
+    }
     seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_time, nullptr, t_rowptr, E, n_t);
     seg_sum_kernel<<<ing_grid(n_t * 32), ING_THREADS, 0, st>>>(t_rowptr, nullptr, t_a, deg_t, n_t);
     cam_runs_sum_kernel<<<ing_grid(n_c * 32), ING_THREADS, 0, st>>>(c_segptr, n_win, n_c, c_order, t_a, deg_c);
@@ -209,7 +236,7 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     VB_CHECK(cudaStreamSynchronize(st));
     const int64_t n_tiles = (int64_t)last_off;
     *h_n_tiles = n_tiles;
-    count_launches(10);   // pair_start, pair_keys, seg_ptr x2, inverse_perm, fold_both, seg_sum, cam_runs_sum, tile_count, tile_fill
+    count_launches(9 + n_fold);   // pair_start, pair_keys, seg_ptr x2, inverse_perm, fold_both (per chunk), seg_sum, cam_runs_sum, tile_count, tile_fill
     return 0;
 }
 
@@ -341,8 +368,8 @@ int vb_sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64_t* 
 }
 
 int vb_sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, double* st_w, const int32_t* sc_ptr,
-                 int32_t* sc_idx, double* sc_w, void* workspace, int64_t workspace_bytes, void* stream) {
-    return sell_fill(g, st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w, workspace, workspace_bytes, (cudaStream_t)stream);
+                 int32_t* sc_idx, double* sc_w, int64_t chunks_c, void* workspace, int64_t workspace_bytes, void* stream) {
+    return sell_fill(g, st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w, chunks_c, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, double* x_c, double* x_t, double rtol,

@@ -47,6 +47,8 @@ class HostUpload:
     ``get(name)`` makes the CURRENT stream wait for that array's copy and returns the tensor."""
 
     ORDER = ("cam", "time", "marker", "k_r", "k_t", "R", "t")
+    R_CHUNKS = 8       # the rotations (72 of the 92 bytes per detection) cross PCIe in chunks: the fold of chunk k
+                       # runs under the copy of chunk k + 1 (vb_arrival)
 
     def __init__(self, arrays: dict, dtypes: dict, device):
         self.device = device
@@ -63,11 +65,23 @@ class HostUpload:
                 arrays[name] = src.contiguous()
                 dst[name] = torch.empty(src.shape, dtype=dtypes[name], device=device)
         self.stream.wait_stream(cur)
+        self.r_chunks = None
         with torch.cuda.stream(self.stream):
             for name in self.ORDER:
                 if name not in dst:
                     continue
-                dst[name].copy_(arrays[name], non_blocking=True)
+                n = dst[name].shape[0]
+                if name == "R" and n >= 64 * self.R_CHUNKS:
+                    ends, evs = [], []
+                    for k in range(self.R_CHUNKS):
+                        lo, hi = n * k // self.R_CHUNKS, n * (k + 1) // self.R_CHUNKS
+                        dst[name][lo:hi].copy_(arrays[name][lo:hi], non_blocking=True)
+                        e = torch.cuda.Event()
+                        e.record(self.stream)
+                        ends.append(hi); evs.append(e)
+                    self.r_chunks = (ends, evs)
+                else:
+                    dst[name].copy_(arrays[name], non_blocking=True)
                 dst[name].record_stream(self.stream)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
@@ -75,6 +89,10 @@ class HostUpload:
 
     def get(self, name):
         torch.cuda.current_stream(self.device).wait_event(self._ev[name])
+        return self._t[name]
+
+    def peek(self, name):
+        """The destination tensor WITHOUT waiting for its copy (the consumer synchronises itself)."""
         return self._t[name]
 
 
@@ -136,14 +154,24 @@ class DeviceGraph:
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             self.raw_perm = torch.empty(n_raw, dtype=I32, device=dev)
             self.raw_pair = torch.empty(n_raw, dtype=I32, device=dev)
-            npairs = C.c_int64(0)
+            npairs, was_sorted = C.c_int64(0), C.c_int32(0)
             check(lib.vb_ingest_sort(_ptr(self.cam), _ptr(self.time), n_raw, self.n_c, self.n_t, _ptr(self.raw_perm),
-                                     _ptr(self.raw_pair), C.byref(npairs), _ptr(ws), wsb, _stream()), "vb_ingest_sort")
+                                     _ptr(self.raw_pair), C.byref(npairs), C.byref(was_sorted), _ptr(ws), wsb, _stream()),
+                  "vb_ingest_sort")
             E = int(npairs.value)
             self.n_edges = E
+            arrival = None
             if upload is not None:
                 self.marker, self.k_r, self.k_t = upload.get("marker"), upload.get("k_r"), upload.get("k_t")
-                R = upload.get("R").reshape(-1, 9)
+                if upload.r_chunks is not None:
+                    # the rotations are still in flight: hand the extension their arrival schedule instead of waiting
+                    ends, evs = upload.r_chunks
+                    self._arr_ends = (C.c_int64 * len(ends))(*ends)
+                    self._arr_evs = (C.c_void_p * len(evs))(*[e.cuda_event for e in evs])
+                    arrival = _cabi.VbArrival(len(ends), int(was_sorted.value), self._arr_ends, self._arr_evs)
+                    R = upload.peek("R").reshape(-1, 9)
+                else:
+                    R = upload.get("R").reshape(-1, 9)
             else:
                 self.marker = _dev(marker, I32, dev)
                 R = _dev(R, F64, dev).reshape(-1, 9)
@@ -184,7 +212,8 @@ class DeviceGraph:
                 _ptr(self.t_a), _ptr(self.t_w), _ptr(self.pair_start), _ptr(self.c_segptr), _ptr(self.c_time),
                 _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_order), _ptr(self.tile_cam),
                 _ptr(self.tile_start),
-                _ptr(self.tile_off), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c), _ptr(ws), wsb, _stream()),
+                _ptr(self.tile_off), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c),
+                C.byref(arrival) if arrival is not None else None, _ptr(ws), wsb, _stream()),
                 "vb_ingest_build")
             self.n_tiles = int(ntiles.value)
             self.tile_part = e((max(self.n_tiles, 1), 9), F64)      # camera-pass scratch (per-tile sums)
@@ -219,7 +248,7 @@ class DeviceGraph:
             sc_idx = torch.empty(32 * max(int(cc.value), 1), dtype=I32, device=dev)
             sc_w = torch.empty(32 * max(int(cc.value), 1), dtype=F64, device=dev)
             check(lib.vb_sell_fill(C.byref(self.cgraph), _ptr(st_ptr), _ptr(st_idx), _ptr(st_w), _ptr(sc_ptr),
-                                   _ptr(sc_idx), _ptr(sc_w), _ptr(ws), wsb, _stream()), "vb_sell_fill")
+                                   _ptr(sc_idx), _ptr(sc_w), int(cc.value), _ptr(ws), wsb, _stream()), "vb_sell_fill")
         self._sell = (st_ptr, st_idx, st_w, sc_ptr, sc_idx, sc_w)
         self.sell_chunks = (int(ct.value), int(cc.value))
         g = self.cgraph
