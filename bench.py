@@ -437,9 +437,9 @@ def main():
     share = {k: (n_time if "time" in k else n_cam) * v["ms"] / phases[-1]["rotation"] for k, v in kern.items()}
     dom = max(kern, key=lambda k: share[k])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "traffic": 3.98e9 if "time" in dom else 4.01e9,
+                "frac": kern[dom]["gbs"] / peak, "traffic": 4.060e9 if "time" in dom else 4.017e9,
                 "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch on cfg4 at 1 GPU "
-                                  "(profiles/r1_edge_pass_history.md, capture prof_passes_r1e)",
+                                  "(profiles/r2_edge_pass.md, capture prof_passes_r2b)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kern[dom]["bytes"], "ms_per_launch": kern[dom]["ms"],
                 "measured": "CUDA events around every executed launch inside the timed steps",
