@@ -60,62 +60,12 @@ __global__ void make_keys_kernel(const int* __restrict__ major, const int* __res
     vals[i] = (int)i;
 }
 
-__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int* __restrict__ flags, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-}
-
-__global__ void pair_ids_kernel(const int* __restrict__ incl, int* __restrict__ pair, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    pair[i] = incl[i] - 1;
-}
-
 __global__ void pair_start_kernel(const int* __restrict__ raw_pair, int* __restrict__ pair_start, int64_t n_raw, int64_t n_pairs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_raw) return;
     const int p = raw_pair[i];
     if (i == 0 || raw_pair[i - 1] != p) pair_start[p] = (int)i;
     if (i == n_raw - 1) pair_start[n_pairs] = (int)n_raw;
-}
-
-// One thread per aggregated pair: fold the constraint and sum in original detection order.
-// (A 9-threads-per-pair variant with coalesced 72-byte accesses was measured SLOWER: the index
-// loads are repeated by every thread and dominate when pairs hold one or two detections.)
-__global__ void fold_aggregate_kernel(const int* __restrict__ cam, const int* __restrict__ time, const int* __restrict__ marker,
-                                      const double* __restrict__ R, const double* __restrict__ k_r, const double* __restrict__ k_t,
-                                      const double* __restrict__ markerC, int round_f32, const int* __restrict__ raw_perm,
-                                      const int* __restrict__ pair_start, int64_t n_pairs, int* __restrict__ t_cam,
-                                      int* __restrict__ t_time, double* __restrict__ t_B, double* __restrict__ t_a, double* __restrict__ t_w) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    const int s = pair_start[p], e = pair_start[p + 1];
-    double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double a = 0.0, w = 0.0;
-    for (int pos = s; pos < e; ++pos) {
-        const int64_t r = raw_perm[pos];
-        const double kr = k_r[r], kt = k_t[r];
-        double kR[9], C[9], blk[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const double v = R[9 * r + i];
-            kR[i] = round_f32 ? (double)((float)kr * (float)v) : kr * v;
-            C[i] = markerC[9 * (int64_t)marker[r] + i];
-        }
-        mm3(kR, C, blk);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) B[i] += blk[i];
-        a += kr;
-        w += kt * kt;
-    }
-    const int64_t r0 = raw_perm[s];
-    t_cam[p] = cam[r0];
-    t_time[p] = time[r0];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) t_B[9 * p + i] = B[i];
-    t_a[p] = a;
-    t_w[p] = w;
 }
 
 // Per aggregated pair: its endpoints and its key in the camera-pass order, key = window(time) * n_c + cam
@@ -211,11 +161,6 @@ fold_both_kernel(const int* __restrict__ marker, const double* __restrict__ R, c
     }
 }
 
-__global__ void check_sorted_kernel(const uint64_t* __restrict__ keys, int64_t n, int* __restrict__ unsorted_flag) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 < n && keys[i] > keys[i + 1]) *unsorted_flag = 1;
-}
-
 __global__ void iota_kernel(int* __restrict__ v, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = (int)i;
@@ -231,22 +176,6 @@ __global__ void seg_ptr_kernel(const int* __restrict__ node_sorted, const int* _
     for (int v = prev + 1; v <= cur; ++v) ptr[v] = (int)i;
     if (i == n - 1)
         for (int64_t v = cur + 1; v <= n_nodes; ++v) ptr[v] = (int)n;
-}
-
-__global__ void gather_cam_sorted_kernel(const int* __restrict__ c_perm, const int* __restrict__ t_time, const double* __restrict__ t_B,
-                                         const double* __restrict__ t_w, int* __restrict__ c_time, double* __restrict__ c_B,
-                                         double* __restrict__ c_w, int64_t n) {
-    // 9 threads per edge: coalesced 72-byte record copies.  The camera-pass copy holds the blocks
-    // TRANSPOSED: the camera pass needs COLUMN k of B_e per lane, and with B^T in the stage that is a
-    // contiguous row (conflict-free LDS.64, like the time pass) instead of a stride-3 column whose
-    // shared-memory reads were 2-way bank conflicted (30 M of 156 M L1 wavefronts per pass, ncu)
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t i = gid / 9;
-    const int k = (int)(gid - 9 * i);
-    if (i >= n) return;
-    const int64_t src = c_perm[i];
-    c_B[9 * i + k] = t_B[9 * src + 3 * (k % 3) + k / 3];
-    if (k == 0) { c_time[i] = t_time[src]; c_w[i] = t_w[src]; }
 }
 
 // warp per node: deg[v] = sum of a over its segment (optionally through a permutation)
@@ -282,27 +211,6 @@ __global__ void tile_fill_kernel(const int* __restrict__ colptr, const int* __re
         tile_start[t] = b;
     }
     if (c == n_seg - 1) tile_start[off[n_seg]] = e;
-}
-
-// key = window(time) * n_c + cam: camera-pass order.  The input (aggregated pairs) is already
-// sorted by (time, camera) and the radix sort is stable, so the result is ordered by
-// (window, camera, time) with only log2(n_win * n_c) key bits.  Tiles of all cameras that fall in
-// the same time window are adjacent in the stream, so the W records gathered by concurrently
-// running warps come from one window of W (L2 resident) instead of all of it.
-__global__ void make_window_keys_kernel(const int* __restrict__ cam, const int* __restrict__ time, int64_t n_c, int64_t n_t,
-                                        int64_t n_win, uint64_t* __restrict__ keys, int* __restrict__ vals, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t t = (uint64_t)time[i];
-    const uint64_t win = t * (uint64_t)n_win / (uint64_t)n_t;
-    keys[i] = win * (uint64_t)n_c + (uint64_t)cam[i];
-    vals[i] = (int)i;
-}
-
-__global__ void window_seg_kernel(const uint64_t* __restrict__ keys_sorted, int* __restrict__ seg, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    seg[i] = (int)keys_sorted[i];
 }
 
 // warp per camera: out[c] = sum over the camera's (window, camera) runs of a[order[i]] -- the

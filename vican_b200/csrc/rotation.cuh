@@ -146,14 +146,6 @@ __global__ void __launch_bounds__(1024) deflate_kernel(const double* __restrict_
     }
 }
 
-// Y = 0 unless the convergence flag is set (speculative camera passes must leave Y alone once the
-// eigen-iteration has converged: the shortcut below reuses it)
-__global__ void cond_zero_kernel(double* __restrict__ Y, int64_t n, const double* __restrict__ skip_flag) {
-    if (skip_flag != nullptr && *skip_flag != 0.0) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) Y[i] = 0.0;
-}
-
 // bipgo.py:306-315
 __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const double* __restrict__ M, double* __restrict__ r_c, double* __restrict__ lamC,
                                      double* __restrict__ lamCinv, int64_t n_c, double* __restrict__ r12 = nullptr) {
