@@ -189,12 +189,13 @@ inline int sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     const int64_t ns_t = sell_slices(n_t), ns_c = sell_slices(n_c);
     int tot_t = 0, tot_c = 0;
+    if (pinned_scalars() == nullptr) return -(int)cudaErrorMemoryAllocation;
     if (n_t > 0) {
         sell_row_len_time_kernel<<<(int)((n_t + 255) / 256), 256, 0, st>>>(g->t_rowptr, n_t, w.len_t);
         sell_count_kernel<<<(int)((ns_t + 256) / 256), 256, 0, st>>>(w.len_t, n_t, ns_t, w.cnt_t);
         size_t tb = w.cub_bytes;
         VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.cnt_t, st_ptr, (int)(ns_t + 1), st));
-        VB_CHECK(cudaMemcpyAsync(&tot_t, st_ptr + ns_t, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VB_CHECK(cudaMemcpyAsync(pinned_scalars(), st_ptr + ns_t, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     sell_row_len_cam_kernel<<<(int)((n_c + 255) / 256), 256, 0, st>>>(g->c_segptr, g->n_windows, n_c, w.len_c);
     sell_count_kernel<<<(int)((ns_c + 256) / 256), 256, 0, st>>>(w.len_c, n_c, ns_c, w.cnt_c);
@@ -202,9 +203,11 @@ inline int sell_count(const vb_graph* g, int32_t* st_ptr, int32_t* sc_ptr, int64
         size_t tb = w.cub_bytes;
         VB_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, (const int*)w.cnt_c, sc_ptr, (int)(ns_c + 1), st));
     }
-    VB_CHECK(cudaMemcpyAsync(&tot_c, sc_ptr + ns_c, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VB_CHECK(cudaMemcpyAsync(pinned_scalars() + 1, sc_ptr + ns_c, sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_KERNEL_CHECK();
     VB_CHECK(cudaStreamSynchronize(st));
+    if (n_t > 0) tot_t = *(const int*)pinned_scalars();
+    tot_c = *(const int*)(pinned_scalars() + 1);
     count_launches(n_t > 0 ? 4 : 2);
     *h_chunks_t = tot_t;
     *h_chunks_c = tot_c;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -30,6 +31,28 @@ inline std::atomic<long long>& launch_counter() {
     return c;
 }
 inline void count_launches(long long n) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
+
+// Small pinned host buffer for scalar read-backs (a device-to-host copy into pageable memory is staged by the
+// driver and costs tens of microseconds more per synchronisation than one into pinned memory)
+inline long long* pinned_scalars() {
+    static thread_local long long* p = nullptr;
+    if (p == nullptr && cudaMallocHost((void**)&p, 128 * sizeof(long long)) != cudaSuccess) p = nullptr;
+    return p;
+}
+// copy n bytes (<= 1 KB) from the device to *dst through the pinned buffer and synchronise the stream
+inline cudaError_t read_back(void* dst, const void* d_src, size_t n, cudaStream_t st) {
+    long long* h = pinned_scalars();
+    if (h == nullptr || n > 128 * sizeof(long long)) {
+        cudaError_t e = cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+    }
+    cudaError_t e = cudaMemcpyAsync(h, d_src, n, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    memcpy(dst, h, n);
+    return cudaSuccess;
+}
 
 inline int sm_count() {
     static int n = 0;

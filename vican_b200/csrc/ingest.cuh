@@ -303,8 +303,7 @@ inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n
     VB_CHECK(cudaMemsetAsync(w.tmp_a, 0, sizeof(int), st));
     check_sorted_ct_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(time, cam, n_raw, w.tmp_a);
     int unsorted = 0;
-    VB_CHECK(cudaMemcpyAsync(&unsorted, w.tmp_a, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CHECK(cudaStreamSynchronize(st));
+    VB_CHECK(read_back(&unsorted, w.tmp_a, sizeof(int), st));
     size_t tb = w.cub_bytes;
     thrust::counting_iterator<int> iota(0);
     if (unsorted) {
@@ -321,8 +320,7 @@ inline int ingest_sort(const int* cam, const int* time, int64_t n_raw, int64_t n
     }
     VB_KERNEL_CHECK();
     int last = 0;
-    VB_CHECK(cudaMemcpyAsync(&last, raw_pair + (n_raw - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CHECK(cudaStreamSynchronize(st));
+    VB_CHECK(read_back(&last, raw_pair + (n_raw - 1), sizeof(int), st));
     *h_n_pairs = (int64_t)last + 1;
     if (h_sorted) *h_sorted = unsorted ? 0 : 1;
     count_launches(unsorted ? 2 : 2);   // check_sorted + (make_keys | iota); CUB's sort / scan are library kernels

@@ -206,8 +206,7 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
         int64_t* d_tmp = (int64_t*)w.keys_a;   // keys_a is free again (the sort has consumed it)
         VB_CHECK(cudaMemcpyAsync(d_tmp, arrival->h_raw_end, n_fold * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         chunk_pairs_kernel<<<1, 64, 0, st>>>(raw_pair, d_tmp, n_fold, n_raw, E, d_tmp + 64);
-        VB_CHECK(cudaMemcpyAsync(h_pair_end, d_tmp + 64, n_fold * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        VB_CHECK(cudaStreamSynchronize(st));
+        VB_CHECK(read_back(h_pair_end, d_tmp + 64, n_fold * sizeof(int64_t), st));
         h_pair_end[n_fold - 1] = E;
     }
     int64_t p_lo = 0;
@@ -232,8 +231,7 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
     tile_fill_kernel<<<ing_grid(n_seg), ING_THREADS, 0, st>>>(c_segptr, tile_off, tile_cam, tile_start, n_seg, n_c, (int)tile_len);
     VB_KERNEL_CHECK();
     int last_off = 0;
-    VB_CHECK(cudaMemcpyAsync(&last_off, tile_off + n_seg, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CHECK(cudaStreamSynchronize(st));
+    VB_CHECK(read_back(&last_off, tile_off + n_seg, sizeof(int), st));
     const int64_t n_tiles = (int64_t)last_off;
     *h_n_tiles = n_tiles;
     count_launches(9 + n_fold);   // pair_start, pair_keys, seg_ptr x2, inverse_perm, fold_both (per chunk), seg_sum, cam_runs_sum, tile_count, tile_fill
@@ -253,14 +251,12 @@ int vb_count_components(const vb_graph* g, const int32_t* t_time, int32_t* label
         cc_jump_kernel<<<ing_grid(n), ING_THREADS, 0, st>>>(labels, n);
         launches += 2;
         int changed = 0;
-        VB_CHECK(cudaMemcpyAsync(&changed, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-        VB_CHECK(cudaStreamSynchronize(st));
+        VB_CHECK(read_back(&changed, flag, sizeof(int), st));
         if (!changed) break;
     }
     cc_count_kernel<<<ing_grid(n), ING_THREADS, 0, st>>>(labels, n, flag + 1);
     int count = 0;
-    VB_CHECK(cudaMemcpyAsync(&count, flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CHECK(cudaStreamSynchronize(st));
+    VB_CHECK(read_back(&count, flag + 1, sizeof(int), st));
     VB_KERNEL_CHECK();
     count_launches(launches + 1);
     *h_count = count;
