@@ -445,3 +445,22 @@ def test_early_exit_on_a_disconnected_graph_like_the_reference(cuda):
     # the gauge camera's component is determined: its cameras agree with the oracle
     for c in range(6):
         assert geodesic_rad(out[str(c)].R(), ref[str(c)][0]).max() <= ROT_TOL_RAD
+
+
+def test_stalled_eigen_iteration_is_reported(cuda, monkeypatch):
+    """An eigen-iteration that stops at its step cap must not pass silently (the reference's ARPACK call raises
+    ArpackNoConvergence there): EigenConvergenceWarning by default, ConvergenceError with strict=True."""
+    import warnings
+    from vican_b200 import bipgo, solver
+    g = syn.make_camera_network(9, 12, 60, 3, 4, 2)
+    edges, constraints = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = callables(True)
+    real = solver.solve_rotations
+    monkeypatch.setattr(solver, "solve_rotations", lambda gg, maxiter, **kw: real(gg, maxiter, **dict(kw, max_inner=2)))
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        out = bipgo.bipartite_se3sync(edges, constraints, nr, nt, ef, 3, "conjugate_gradient", dtype=np.float64)
+    assert any(issubclass(w.category, bipgo.EigenConvergenceWarning) for w in wlist)
+    assert bipgo.last_info["eig_status"] == 2 and len(out) == 12 + 60
+    with pytest.raises(solver.ConvergenceError):
+        bipgo.bipartite_se3sync(edges, constraints, nr, nt, ef, 3, "conjugate_gradient", dtype=np.float64, strict=True)
