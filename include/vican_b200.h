@@ -279,11 +279,14 @@ int vb_trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t, dou
 int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw);
 /* LSQR on J x = t~ replaying scipy.sparse.linalg.lsqr defaults (bipgo.py:480: damp 0,
  * atol = btol = 1e-6, conlim 1e8, iter_lim = 2 * 3N).  Rows are the raw detections in sorted
- * order: k_t (x_t - x_c) = k_t d_e. */
+ * order: k_t (x_t - x_c) = k_t d_e.  allreduce != NULL (edge-sharded runs): rows and time nodes are local, the
+ * camera block is replicated; three collectives per bidiagonalisation step (||u||^2; the camera part of A^T u;
+ * ||v_t||^2 and ||w_t||^2 together). */
 int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw_pair, const int32_t* pair_start,
                   const int32_t* t_time, const double* k_t, const double* d_sorted, int64_t n_raw, double* x_c, double* x_t,
                   double atol, double btol, double conlim, int64_t iter_lim, int32_t* h_istop,
-                  int32_t* h_iters, void* workspace, int64_t workspace_bytes, void* stream);
+                  int32_t* h_iters, void* workspace, int64_t workspace_bytes, vb_allreduce_fn allreduce,
+                  void* allreduce_ctx, void* stream);
 
 /* Dense direct solve of the same normal equations for small camera sets (n_c <= 8192; the
  * "direct" option in accurate mode): time nodes are eliminated in closed form, the n_c x n_c camera

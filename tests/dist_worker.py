@@ -113,6 +113,16 @@ def main_gpu():
         print("DIST_GPU world=%d collective=%s rot_c=%.2e rot_t=%.2e x_c=%.2e x_t=%.2e cg_iters=%d/%d" %
               (world, "peer(fused)" if comm.peer is not None else "nccl", ec, et, xc, xt, res.trans.iters, ref.trans.iters))
         ok = ec < 1e-9 and et < 1e-9 and xc < 1e-8 and xt < 1e-8 and res.trans.iters == ref.trans.iters
+    # lsqr_solver="direct" (LSQR replay) on the same shards: three collectives per bidiagonalisation step
+    tr_d = solver.solve_translations(res.graph, res.rot, det.t, q0, "direct", comm=comm)
+    parts_d = [torch.empty((p.shape[0], 3), dtype=torch.float64, device=dev) for p in parts_R]
+    dist.all_gather(parts_d, tr_d.x_t.contiguous())
+    if rank == 0:
+        ref_d = solver.solve_translations(ref.graph, ref.rot, full.t, q0, "direct")
+        dc = rel_translation_err(tr_d.x_c.cpu().numpy(), ref_d.x_c.cpu().numpy()).max()
+        dt = rel_translation_err(torch.cat(parts_d).cpu().numpy(), ref_d.x_t.cpu().numpy()).max()
+        print("DIST_GPU direct: x_c=%.2e x_t=%.2e itn=%d/%d istop=%d/%d" % (dc, dt, tr_d.iters, ref_d.iters, tr_d.istop, ref_d.istop))
+        ok = ok and dc < 1e-6 and dt < 1e-6 and tr_d.iters == ref_d.iters and tr_d.istop == ref_d.istop
         print("DIST_GPU_OK" if ok else "DIST_GPU_FAIL")
     vdist.destroy_comm(comm)
     dist.barrier()

@@ -101,7 +101,7 @@ SIGNATURES = {
                               C.c_int, VP]),
     "vb_trans_lsqr_workspace_bytes": (I64, [I64, I64, I64]),
     "vb_trans_lsqr": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, I64, VP, VP, F64, F64, F64, I64,
-                                c_i32p, c_i32p, VP, I64, VP]),
+                                c_i32p, c_i32p, VP, I64, VP, VP, VP]),
     "vb_trans_schur_workspace_bytes": (I64, [I64, I64]),
     "vb_trans_schur_direct": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, I64, VP]),
     "vb_nccl_available": (C.c_int, []),

@@ -15,7 +15,7 @@ enum { LS_ALFA = 0, LS_BETA, LS_RHOBAR, LS_PHIBAR, LS_ANORM, LS_DDNORM, LS_XXNOR
        LS_NSCAL = 32 };
 
 struct LsqrWork {
-    double *u, *v_c, *v_t, *w_c, *w_t, *kt_sorted, *partial, *sc;
+    double *u, *v_c, *v_t, *w_c, *w_t, *kt_sorted, *partial, *sc, *acc_c;
     int *row_cam, *row_time, *cam_rows, *cam_ptr;
     uint64_t *keys_a, *keys_b;
     int* vals_a;
@@ -40,6 +40,7 @@ inline LsqrWork carve_lsqr(void* base, int64_t n_c, int64_t n_t, int64_t n_raw) 
     w.w_c = (double*)take(8 * 3 * n_c); w.w_t = (double*)take(8 * 3 * n_t);
     w.kt_sorted = (double*)take(8 * n_raw);
     w.partial = (double*)take(8 * LS_MAX_PARTIAL);
+    w.acc_c = (double*)take(8 * (3 * n_c + 8));
     w.sc = (double*)take(8 * LS_NSCAL);
     w.row_cam = (int*)take(4 * n_raw); w.row_time = (int*)take(4 * n_raw);
     w.cam_rows = (int*)take(4 * n_raw); w.cam_ptr = (int*)take(4 * (n_c + 1));
@@ -134,9 +135,12 @@ __global__ void lsqr_vt_kernel(const int* __restrict__ t_rowptr, const int* __re
     }
 }
 
-// camera side (u already normalised): warp per camera over its rows in ascending row order
+// camera side (u already normalised): warp per camera over its rows in ascending row order.
+// acc_out != nullptr (edge-sharded runs): only the local row sums are written there; they are summed over the
+// ranks and lsqr_vc_finish_kernel applies  v_c = sum - beta v_c.
 __global__ void lsqr_vc_kernel(const int* __restrict__ cam_ptr, const int* __restrict__ cam_rows, const double* __restrict__ kt,
-                               const double* __restrict__ u, double* __restrict__ v_c, int64_t n_c, const double* sc, int init) {
+                               const double* __restrict__ u, double* __restrict__ v_c, int64_t n_c, const double* sc, int init,
+                               double* __restrict__ acc_out) {
     if (sc[LS_ISTOP] != 0.0) return;
     const int lane = threadIdx.x & 31;
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -150,10 +154,22 @@ __global__ void lsqr_vc_kernel(const int* __restrict__ cam_ptr, const int* __res
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) {
-        if (init) { v_c[3 * c] = a0; v_c[3 * c + 1] = a1; v_c[3 * c + 2] = a2; }
+        if (acc_out) { acc_out[3 * c] = a0; acc_out[3 * c + 1] = a1; acc_out[3 * c + 2] = a2; }
+        else if (init) { v_c[3 * c] = a0; v_c[3 * c + 1] = a1; v_c[3 * c + 2] = a2; }
         else { v_c[3 * c] = a0 - beta * v_c[3 * c]; v_c[3 * c + 1] = a1 - beta * v_c[3 * c + 1]; v_c[3 * c + 2] = a2 - beta * v_c[3 * c + 2]; }
     }
 }
+
+__global__ void lsqr_vc_finish_kernel(const double* __restrict__ acc, double* __restrict__ v_c, int64_t n3, const double* sc, int init) {
+    if (sc[LS_ISTOP] != 0.0) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3) return;
+    v_c[i] = init ? acc[i] : acc[i] - sc[LS_BETA] * v_c[i];
+}
+
+// edge-sharded runs: fixed-order sum of a partial range into one slot / copy of one slot (single thread)
+__global__ void lsqr_collapse_kernel(const double* partial, int nb, double* dst) { *dst = sum_partials(partial, 0, nb); }
+__global__ void lsqr_set_kernel(double* dst, const double* src) { *dst = *src; }
 
 // scalar step 1: beta = ||u||, anorm update.  init: beta = bnorm.
 __global__ void lsqr_s1_kernel(double* sc, const double* partial, int nb, int init) {

@@ -383,12 +383,18 @@ int64_t vb_trans_lsqr_workspace_bytes(int64_t n_c, int64_t n_t, int64_t n_raw) {
 int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw_pair, const int32_t* pair_start,
                   const int32_t* t_time, const double* k_t, const double* d_sorted, int64_t n_raw, double* x_c,
                   double* x_t, double atol, double btol, double conlim, int64_t iter_lim, int32_t* h_istop,
-                  int32_t* h_iters, void* workspace, int64_t workspace_bytes, void* stream) {
+                  int32_t* h_iters, void* workspace, int64_t workspace_bytes, vb_allreduce_fn allreduce,
+                  void* allreduce_ctx, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_c = g->n_c, n_t = g->n_t;
     LsqrWork w = carve_lsqr(workspace, n_c, n_t, n_raw);
     if (w.bytes > workspace_bytes) return VB_STATUS_BAD_ARGUMENT;
     double* hs = pinned_status();
+    const bool multi = allreduce != nullptr;
+    // edge-sharded runs: rows (detections) and time nodes are local, the camera block is replicated.  The three
+    // local norms are collapsed to scalars red[0..2] = ||u||^2, ||v_t||^2, ||w_t||^2 and summed over the ranks;
+    // the camera part of A^T u is summed as a vector.  3 collectives per bidiagonalisation step.
+    double* red = w.partial + 2048;
     lsqr_clear_kernel<<<1, 1, 0, st>>>(w.sc);
     lsqr_rows_kernel<<<tr_grid(n_raw), TR_THREADS, 0, st>>>(raw_perm, raw_pair, g->t_cam, t_time, k_t, d_sorted, n_raw,
                                                            w.row_cam, w.row_time, w.kt_sorted, w.u, w.keys_a, w.vals_a);
@@ -401,33 +407,69 @@ int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw
     seg_ptr_kernel<<<ing_grid(n_raw), ING_THREADS, 0, st>>>(w.row_cam, w.cam_rows, w.cam_ptr, n_raw, n_c);
     VB_KERNEL_CHECK();
     const int nb_u = sumsq_grid(3 * n_raw), nb_c = sumsq_grid(3 * n_c), nb_t = sumsq_grid(3 * n_t);
-    auto v_step = [&](int init) -> int {
+    long long launches = 3;
+    auto u_norm = [&](int init) -> int {   // beta = ||u||
+        sumsq_partial_kernel<<<nb_u, TR_THREADS, 0, st>>>(w.u, 3 * n_raw, 1.0, w.partial);
+        if (multi) {
+            lsqr_collapse_kernel<<<1, 1, 0, st>>>(w.partial, nb_u, red);
+            int rc = allreduce(allreduce_ctx, red, 3, (void*)st);
+            if (rc) return rc;
+            lsqr_set_kernel<<<1, 1, 0, st>>>(w.partial, red);
+            launches += 2;
+        }
+        lsqr_s1_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, multi ? 1 : nb_u, init);
+        launches += 2;
+        return 0;
+    };
+    auto v_step = [&](int init, bool with_w) -> int {   // v = A^T u - beta v, alfa = ||v||
         lsqr_vt_kernel<<<tr_warp_grid(n_t), TR_THREADS, 0, st>>>(g->t_rowptr, pair_start, w.kt_sorted, w.u, w.v_t, n_t, w.sc, init);
-        lsqr_vc_kernel<<<tr_warp_grid(n_c), TR_THREADS, 0, st>>>(w.cam_ptr, w.cam_rows, w.kt_sorted, w.u, w.v_c, n_c, w.sc, init);
+        lsqr_vc_kernel<<<tr_warp_grid(n_c), TR_THREADS, 0, st>>>(w.cam_ptr, w.cam_rows, w.kt_sorted, w.u, w.v_c, n_c, w.sc, init,
+                                                                 multi ? w.acc_c : nullptr);
+        launches += 2;
+        if (multi) {
+            int rc = allreduce(allreduce_ctx, w.acc_c, 3 * n_c, (void*)st);
+            if (rc) return rc;
+            lsqr_vc_finish_kernel<<<tr_grid(3 * n_c), TR_THREADS, 0, st>>>(w.acc_c, w.v_c, 3 * n_c, w.sc, init);
+            // local time parts of ||v||^2 and (when the step needs it) ||w_old||^2, one collective
+            sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.v_t, 3 * n_t, 1.0, w.partial + 1024);
+            lsqr_collapse_kernel<<<1, 1, 0, st>>>(w.partial + 1024, nb_t, red + 1);
+            if (with_w) {
+                sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.w_t, 3 * n_t, 1.0, w.partial + 1024);
+                lsqr_collapse_kernel<<<1, 1, 0, st>>>(w.partial + 1024, nb_t, red + 2);
+            }
+            rc = allreduce(allreduce_ctx, red, 3, (void*)st);   // red[0] is summed again: it is not read any more
+            if (rc) return rc;
+            lsqr_set_kernel<<<1, 1, 0, st>>>(w.partial + 1024, red + 1);
+            launches += with_w ? 6 : 4;
+        } else {
+            sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.v_t, 3 * n_t, 1.0, w.partial + 1024);
+            launches += 1;
+        }
         sumsq_partial_kernel<<<nb_c, TR_THREADS, 0, st>>>(w.v_c, 3 * n_c, 1.0, w.partial);
-        sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.v_t, 3 * n_t, 1.0, w.partial + 1024);
-        lsqr_s2_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_c, nb_t, init);
+        lsqr_s2_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_c, multi ? 1 : nb_t, init);
+        launches += 2;
         VB_KERNEL_CHECK();
         return 0;
     };
     // initial bidiagonalisation vectors (lsqr.py:372-398)
-    sumsq_partial_kernel<<<nb_u, TR_THREADS, 0, st>>>(w.u, 3 * n_raw, 1.0, w.partial);
-    lsqr_s1_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_u, 1);
-    { int rc = v_step(1); if (rc) return rc; }
+    { int rc = u_norm(1); if (rc) return rc; }
+    { int rc = v_step(1, false); if (rc) return rc; }
     lsqr_x_kernel<<<tr_grid(3 * n_c), TR_THREADS, 0, st>>>(w.v_c, w.w_c, x_c, 3 * n_c, w.sc, 1);
     lsqr_x_kernel<<<tr_grid(3 * n_t), TR_THREADS, 0, st>>>(w.v_t, w.w_t, x_t, 3 * n_t, w.sc, 1);
     VB_KERNEL_CHECK();
+    launches += 2;
     for (int64_t it = 0; it < iter_lim; ++it) {
         lsqr_u_kernel<<<tr_grid(n_raw), TR_THREADS, 0, st>>>(w.row_cam, w.row_time, w.kt_sorted, w.v_c, w.v_t, w.u, n_raw, w.sc);
-        sumsq_partial_kernel<<<nb_u, TR_THREADS, 0, st>>>(w.u, 3 * n_raw, 1.0, w.partial);
-        lsqr_s1_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_u, 0);
-        { int rc = v_step(0); if (rc) return rc; }
+        { int rc = u_norm(0); if (rc) return rc; }
+        { int rc = v_step(0, true); if (rc) return rc; }
         sumsq_partial_kernel<<<nb_c, TR_THREADS, 0, st>>>(w.w_c, 3 * n_c, 1.0, w.partial);
-        sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.w_t, 3 * n_t, 1.0, w.partial + 1024);
+        if (multi) lsqr_set_kernel<<<1, 1, 0, st>>>(w.partial + 1024, red + 2);
+        else sumsq_partial_kernel<<<nb_t, TR_THREADS, 0, st>>>(w.w_t, 3 * n_t, 1.0, w.partial + 1024);
         lsqr_x_kernel<<<tr_grid(3 * n_c), TR_THREADS, 0, st>>>(w.v_c, w.w_c, x_c, 3 * n_c, w.sc, 0);
         lsqr_x_kernel<<<tr_grid(3 * n_t), TR_THREADS, 0, st>>>(w.v_t, w.w_t, x_t, 3 * n_t, w.sc, 0);
-        lsqr_s3_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_c, nb_t, atol, btol, conlim, (double)iter_lim);
+        lsqr_s3_kernel<<<1, 1, 0, st>>>(w.sc, w.partial, nb_c, multi ? 1 : nb_t, atol, btol, conlim, (double)iter_lim);
         VB_KERNEL_CHECK();
+        launches += 6;
         VB_CHECK(cudaMemcpyAsync(hs, w.sc, LS_NSCAL * sizeof(double), cudaMemcpyDeviceToHost, st));
         VB_CHECK(cudaStreamSynchronize(st));
         if (hs[LS_ISTOP] != 0.0) break;
@@ -436,7 +478,7 @@ int vb_trans_lsqr(const vb_graph* g, const int32_t* raw_perm, const int32_t* raw
     VB_CHECK(cudaStreamSynchronize(st));
     if (h_istop) *h_istop = (int32_t)hs[LS_ISTOP];
     if (h_iters) *h_iters = (int32_t)hs[LS_ITN];
-    count_launches(12 + 12 * (long long)hs[LS_ITN]);   // set-up + 12 kernels per bidiagonalisation step
+    count_launches(launches);
     return 0;
 }
 

@@ -479,15 +479,14 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
                                             wsb, _stream()), "vb_trans_schur_direct")
             return TranslationResult(x_c, x_t, 0, 0)
         if need_rows:
-            if comm is not None:
-                raise NotImplementedError("lsqr_solver='direct' is the small-graph path (single GPU)")
             wsb = int(lib.vb_trans_lsqr_workspace_bytes(g.n_c, g.n_t, g.n_raw))
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             n_unknowns = 3 * (g.n_c + g.n_t)
+            fn, fctx = comm.reducer(lib, 3 * g.n_c) if comm is not None else (None, None)
             check(lib.vb_trans_lsqr(C.byref(g.cgraph), _ptr(g.raw_perm), _ptr(g.raw_pair), _ptr(g.pair_start),
                                     _ptr(g.t_time), _ptr(g.k_t), _ptr(d_sorted), g.n_raw, _ptr(x_c), _ptr(x_t),
                                     1e-6, 1e-6, 1e8, 2 * n_unknowns, C.byref(istop), C.byref(iters), _ptr(ws), wsb,
-                                    _stream()), "vb_trans_lsqr")
+                                    fn, fctx, _stream()), "vb_trans_lsqr")
         else:
             if comm is not None and rhs_c is not None:
                 # camera rows of J^T t~ are partial sums over the local edge shard
