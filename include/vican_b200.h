@@ -196,8 +196,9 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
                     int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_off,
                     int64_t* h_n_tiles, double* deg_t, double* deg_c,
-                    const vb_arrival* arrival /* NULL: R is resident */, void* workspace,
-                    int64_t workspace_bytes, void* stream);
+                    const vb_arrival* arrival /* NULL: R is resident */,
+                    int64_t n_markers /* rows of markerC */, int identity_perm /* raw_perm is the identity (h_sorted) */,
+                    void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Number of connected components of the bipartite graph of aggregated edges (min-label hooking + pointer
  * jumping on the device).  labels: scratch [n_c + n_t + 2] int32; t_time [E] = time node of every time-sorted
@@ -247,11 +248,14 @@ int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, do
  *   d_e = Rw_c t_cm + Rw_t q_m,  q_m = (R_0^T R_m) (T_m^-1 T_0).t   (bipgo.py:451-455),
  * Rw = world rotations (transposes of r_c / r_t).  Also writes d_raw [n_raw][3] in sorted order
  * when non-NULL (needed by LSQR).  rhs = J^T t~ : rhs_c [n_c][3], rhs_t [n_t][3].  r_c_pad: scratch
- * [n_c][vb_gather_stride()] (the camera rotations are gathered from a padded copy with 256-bit loads). */
+ * [n_c][vb_gather_stride()] (the camera rotations are gathered from a padded copy with 256-bit loads).
+ * n_markers = rows of marker_q (<= 256: staged in shared memory); identity_perm != 0: raw_perm is the identity
+ * (vb_ingest_sort's h_sorted) and is not read. */
 int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
                  const double* t_cm, const double* k_t, const double* marker_q, const double* r_c,
                  const double* r_t, const int32_t* t_time, double* pair_g,
-                 double* d_sorted, double* rhs_c, double* rhs_t, double* r_c_pad, void* stream);
+                 double* d_sorted, double* rhs_c, double* rhs_t, double* r_c_pad, int64_t n_markers,
+                 int identity_perm, void* stream);
 /* Sliced-ELL copy of the translation Laplacian for vb_trans_cg (see vb_graph).  vb_sell_count writes the slice
  * pointers (st_ptr [ceil(n_t/8)+2], sc_ptr [ceil(n_c/8)+2]) and returns the chunk totals on the host
  * (synchronises); the caller allocates 32 * chunks slots per side and vb_sell_fill fills them. */

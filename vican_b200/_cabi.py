@@ -78,7 +78,7 @@ SIGNATURES = {
     "vb_ingest_windows": (I64, [I64, I64, I64]),
     "vb_ingest_build": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, I64, C.c_int, VP, VP, I64, I64, I64, I64,
                                   VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, c_i64p, VP, VP,
-                                  C.POINTER(VbArrival), VP, I64, VP]),
+                                  C.POINTER(VbArrival), I64, C.c_int, VP, I64, VP]),
     "vb_count_components": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, VP]),
     "vb_offset_copy_i32": (C.c_int, [VP, VP, I64, I32, VP]),
     "vb_add_inplace_f64": (C.c_int, [VP, VP, I64, VP]),
@@ -92,7 +92,8 @@ SIGNATURES = {
     "vb_so3sync_workspace_bytes": (I64, [I64, I64]),
     "vb_so3sync_run": (C.c_int, [C.POINTER(VbGraph), C.POINTER(VbSo3Options), VP, VP, VP, I64,
                                  C.POINTER(VbSo3Stats), VP]),
-    "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+    "vb_trans_rhs": (C.c_int, [C.POINTER(VbGraph), VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP, I64, C.c_int,
+                               VP]),
     "vb_trans_cg_workspace_bytes": (I64, [I64, I64]),
     "vb_sell_workspace_bytes": (I64, [I64, I64, I64]),
     "vb_sell_count": (C.c_int, [C.POINTER(VbGraph), VP, VP, c_i64p, c_i64p, VP, I64, VP]),

@@ -99,31 +99,40 @@ __global__ void inverse_perm_kernel(const int* __restrict__ c_order, int* __rest
 // stored transposed, one contiguous 72-byte record per pair at its camera-pass position), plus the
 // per-pair weights in both orders.  One thread folds one pair, in original detection order.
 constexpr int FOLD_THREADS = 256;
+constexpr int FOLD_MAX_MARKERS_SMEM = 64;
 __global__ void __launch_bounds__(FOLD_THREADS)
 fold_both_kernel(const int* __restrict__ marker, const double* __restrict__ R, const double* __restrict__ k_r,
                  const double* __restrict__ k_t, const double* __restrict__ markerC, int round_f32,
                  const int* __restrict__ raw_perm, const int* __restrict__ pair_start, int64_t p_begin, int64_t n_pairs,
                  const int* __restrict__ t_time, const int* __restrict__ c_pos, double* __restrict__ t_B,
                  double* __restrict__ t_a, double* __restrict__ t_w, double* __restrict__ c_B, int* __restrict__ c_time,
-                 double* __restrict__ c_w) {
+                 double* __restrict__ c_w, int n_markers, int identity_perm) {
+    // the chain of dependent global loads per pair (pair_start -> raw_perm -> detection -> marker constant) is what
+    // bounds this kernel's latency: the marker constants sit in shared memory, sorted input needs no permutation
+    __shared__ double sC[9 * FOLD_MAX_MARKERS_SMEM];
+    const bool c_smem = n_markers <= FOLD_MAX_MARKERS_SMEM;
+    if (c_smem)
+        for (int i = threadIdx.x; i < 9 * n_markers; i += FOLD_THREADS) sC[i] = markerC[i];
+    const double* mC = c_smem ? sC : markerC;
     __shared__ double sB[FOLD_THREADS * 9];
     __shared__ double sW[FOLD_THREADS];
     __shared__ int sPos[FOLD_THREADS], sTime[FOLD_THREADS];
     const int64_t p0 = p_begin + (int64_t)blockIdx.x * FOLD_THREADS;   // pairs [p_begin, n_pairs) of this launch
     const int64_t p = p0 + threadIdx.x;
+    __syncthreads();
     if (p < n_pairs) {
         const int s = pair_start[p], e = pair_start[p + 1];
         double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         double a = 0.0, w = 0.0;
         for (int pos = s; pos < e; ++pos) {
-            const int64_t r = raw_perm[pos];
+            const int64_t r = identity_perm ? pos : raw_perm[pos];
             const double kr = k_r[r], kt = k_t[r];
             double kR[9], Cm[9], blk[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
                 const double v = R[9 * r + i];
                 kR[i] = round_f32 ? (double)((float)kr * (float)v) : kr * v;
-                Cm[i] = markerC[9 * (int64_t)marker[r] + i];
+                Cm[i] = mC[9 * (int64_t)marker[r] + i];
             }
             mm3(kR, Cm, blk);
 #pragma unroll

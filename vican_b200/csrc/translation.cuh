@@ -24,13 +24,24 @@ inline int tr_grid(int64_t n) { return (int)((n + TR_THREADS - 1) / TR_THREADS);
 inline int tr_warp_grid(int64_t n_warps) { return (int)((n_warps * 32 + TR_THREADS - 1) / TR_THREADS); }
 
 // ------------------------------------------------------------------------------------ RHS
-// thread per pair: g_p = sum k_t^2 d_e,  d_e = r_c^T t_cm + r_t^T q_m   (world rotation = r^T)
+// thread per pair: g_p = sum k_t^2 d_e,  d_e = r_c^T t_cm + r_t^T q_m   (world rotation = r^T).
+// The kernel is bound by the DEPTH of its dependent global loads (ncu: 46 warps per issue on the long scoreboard):
+// pair_start -> raw_perm -> detection -> marker constant.  Two levels are removed where possible: the marker
+// constants sit in shared memory (<= TR_MAX_MARKERS_SMEM markers), and detections that arrived sorted need no
+// permutation (identity_perm: sorted position = raw index).
+constexpr int TR_MAX_MARKERS_SMEM = 256;
 __global__ void trans_pair_kernel(const int* __restrict__ raw_perm, const int* __restrict__ pair_start,
                                   const int* __restrict__ marker, const double* __restrict__ t_cm,
-                                  const double* __restrict__ k_t, const double* __restrict__ marker_q,
+                                  const double* __restrict__ k_t, const double* __restrict__ marker_q_g,
                                   const double* __restrict__ r_c_pad, const double* __restrict__ r_t,
                                   const int* __restrict__ t_cam, const int* __restrict__ t_time, int64_t n_pairs,
-                                  double* __restrict__ pair_g, double* __restrict__ d_sorted) {
+                                  double* __restrict__ pair_g, double* __restrict__ d_sorted, int n_markers, int identity_perm) {
+    __shared__ double sq[3 * TR_MAX_MARKERS_SMEM];
+    const bool q_smem = n_markers <= TR_MAX_MARKERS_SMEM;
+    if (q_smem)
+        for (int i = threadIdx.x; i < 3 * n_markers; i += blockDim.x) sq[i] = marker_q_g[i];
+    __syncthreads();
+    const double* marker_q = q_smem ? sq : marker_q_g;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     double Rc[9], Rt[9];
@@ -44,7 +55,7 @@ __global__ void trans_pair_kernel(const int* __restrict__ raw_perm, const int* _
     for (int i = 0; i < 9; ++i) Rt[i] = r_t[9 * t + i];
     double g0 = 0, g1 = 0, g2 = 0;
     for (int pos = pair_start[p]; pos < pair_start[p + 1]; ++pos) {
-        const int64_t r = raw_perm[pos];
+        const int64_t r = identity_perm ? pos : raw_perm[pos];
         const double tc[3] = {t_cm[3 * r], t_cm[3 * r + 1], t_cm[3 * r + 2]};
         const int64_t m = marker[r];
         const double q[3] = {marker_q[3 * m], marker_q[3 * m + 1], marker_q[3 * m + 2]};

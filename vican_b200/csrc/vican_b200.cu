@@ -172,7 +172,8 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
                     int32_t* t_rowptr, int32_t* t_cam, int32_t* t_time, double* t_B, double* t_a, double* t_w,
                     int32_t* pair_start, int32_t* c_segptr, int32_t* c_time, double* c_B, double* c_w,
                     int32_t* c_order, int32_t* tile_cam, int32_t* tile_start, int32_t* tile_off, int64_t* h_n_tiles, double* deg_t,
-                    double* deg_c, const vb_arrival* arrival, void* workspace, int64_t workspace_bytes, void* stream) {
+                    double* deg_c, const vb_arrival* arrival, int64_t n_markers, int identity_perm, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_raw <= 0 || n_pairs <= 0 || tile_len <= 0) return VB_STATUS_BAD_ARGUMENT;
     if (arrival != nullptr && (arrival->n_chunks < 1 || arrival->n_chunks > 64)) return VB_STATUS_BAD_ARGUMENT;
@@ -218,7 +219,8 @@ int vb_ingest_build(const int32_t* cam, const int32_t* time, const int32_t* mark
         const int64_t p_hi = h_pair_end[kf];
         if (p_hi > p_lo)
             fold_both_kernel<<<(int)((p_hi - p_lo + FOLD_THREADS - 1) / FOLD_THREADS), FOLD_THREADS, 0, st>>>(
-                marker, R, k_r, k_t, markerC, round_kr_f32, raw_perm, pair_start, p_lo, p_hi, t_time, c_pos, t_B, t_a, t_w, c_B, c_time, c_w);
+                marker, R, k_r, k_t, markerC, round_kr_f32, raw_perm, pair_start, p_lo, p_hi, t_time, c_pos, t_B, t_a, t_w, c_B, c_time, c_w,
+                (int)(n_markers > 0x7fffffff ? 0x7fffffff : n_markers), identity_perm);
         p_lo = p_hi > p_lo ? p_hi : p_lo;
     }
     seg_ptr_kernel<<<ing_grid(E), ING_THREADS, 0, st>>>(t_time, nullptr, t_rowptr, E, n_t);
@@ -338,13 +340,14 @@ int vb_so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c, do
 int vb_trans_rhs(const vb_graph* g, const int32_t* raw_perm, const int32_t* pair_start, const int32_t* marker,
                  const double* t_cm, const double* k_t, const double* marker_q, const double* r_c, const double* r_t,
                  const int32_t* t_time, double* pair_g, double* d_sorted, double* rhs_c, double* rhs_t, double* r_c_pad,
-                 void* stream) {
+                 int64_t n_markers, int identity_perm, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t E = g->n_edges;
     if (E <= 0 || r_c_pad == nullptr) return VB_STATUS_BAD_ARGUMENT;
     { int rc = launch_pad_blocks(r_c, r_c_pad, g->n_c, st); if (rc) return rc; }
     trans_pair_kernel<<<tr_grid(E), TR_THREADS, 0, st>>>(raw_perm, pair_start, marker, t_cm, k_t, marker_q, r_c_pad, r_t,
-                                                        g->t_cam, t_time, E, pair_g, d_sorted);
+                                                        g->t_cam, t_time, E, pair_g, d_sorted, (int)(n_markers > 0x7fffffff ? 0x7fffffff : n_markers),
+                                                        identity_perm);
     VB_CHECK(cudaMemsetAsync(rhs_c, 0, 3 * g->n_c * sizeof(double), st));
     VB_CHECK(cudaMemsetAsync(rhs_t, 0, 3 * g->n_t * sizeof(double), st));
     seg_sum3_kernel<<<tr_warp_grid(g->n_t), TR_THREADS, 0, st>>>(g->t_rowptr, nullptr, pair_g, 1.0, rhs_t, g->n_t);

@@ -160,6 +160,7 @@ class DeviceGraph:
                   "vb_ingest_sort")
             E = int(npairs.value)
             self.n_edges = E
+            self.raw_sorted = bool(was_sorted.value)      # raw_perm is the identity
             arrival = None
             if upload is not None:
                 self.marker, self.k_r, self.k_t = upload.get("marker"), upload.get("k_r"), upload.get("k_t")
@@ -213,7 +214,8 @@ class DeviceGraph:
                 _ptr(self.c_B), _ptr(self.c_w), _ptr(self.c_order), _ptr(self.tile_cam),
                 _ptr(self.tile_start),
                 _ptr(self.tile_off), C.byref(ntiles), _ptr(self.deg_t), _ptr(self.deg_c),
-                C.byref(arrival) if arrival is not None else None, _ptr(ws), wsb, _stream()),
+                C.byref(arrival) if arrival is not None else None, int(markerC.shape[0]),
+                1 if self.raw_sorted else 0, _ptr(ws), wsb, _stream()),
                 "vb_ingest_build")
             self.n_tiles = int(ntiles.value)
             self.tile_part = e((max(self.n_tiles, 1), 9), F64)      # camera-pass scratch (per-tile sums)
@@ -298,6 +300,7 @@ class StreamingGraph:
         self.markerC = _dev(markerC, F64, self.device).reshape(-1, 9)
         self.round_kr_f32 = bool(round_kr_f32)
         self.n_t = self.n_edges = self.n_raw = self.n_tiles = self.n_windows = 0
+        self.raw_sorted = True
         self._cap0 = int(capacity_edges)
         self._a = {}
         z = lambda n, dt, w=None: torch.zeros((n,) if w is None else (n, w), dtype=dt, device=self.device)  # noqa: E731
@@ -327,6 +330,7 @@ class StreamingGraph:
                         round_kr_f32=self.round_kr_f32, device=self.device)
         E0, N0, R0, T0, W0 = self.n_edges, self.n_t, self.n_raw, self.n_tiles, self.n_windows
         Ec, Nc, Rc, Tc, Wc, n_c = c.n_edges, c.n_t, c.n_raw, c.n_tiles, c.n_windows, self.n_c
+        self.raw_sorted = self.raw_sorted and c.raw_sorted
         with torch.cuda.device(self.device):
             def put(name, src, lo):                       # plain device-to-device append
                 self._need(name, lo + src.shape[0] + (8 if name in ("t_cam", "c_time") else 2 if name in ("t_B", "c_B") else 0))
@@ -368,6 +372,7 @@ class StreamingGraph:
             raise ValueError("no detections appended yet")
         g.device, g.n_c, g.n_t, g.n_edges, g.n_raw, g.n_tiles, g.n_windows = self.device, self.n_c, N, E, Rn, T, W
         g.tile_len = None
+        g.raw_sorted = self.raw_sorted
         self._need("t_cam", E + 8); self._need("c_time", E + 8); self._need("t_B", E + 2); self._need("c_B", E + 2)
         a = self._a
         for name, n in (("t_cam", E), ("t_time", E), ("t_B", E), ("t_a", E), ("t_w", E), ("c_time", E), ("c_B", E), ("c_w", E),
@@ -464,7 +469,8 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
         r_c_pad = torch.empty((g.n_c, int(lib.vb_gather_stride())), dtype=F64, device=dev)
         check(lib.vb_trans_rhs(C.byref(g.cgraph), _ptr(g.raw_perm), _ptr(g.pair_start), _ptr(g.marker), _ptr(t_cm),
                                _ptr(g.k_t), _ptr(marker_q), _ptr(rot.r_c), _ptr(rot.r_t), _ptr(g.t_time),
-                               _ptr(pair_g), _ptr(d_sorted), _ptr(rhs_c), _ptr(rhs_t), _ptr(r_c_pad), _stream()),
+                               _ptr(pair_g), _ptr(d_sorted), _ptr(rhs_c), _ptr(rhs_t), _ptr(r_c_pad),
+                               int(marker_q.shape[0]), 1 if getattr(g, "raw_sorted", False) else 0, _stream()),
               "vb_trans_rhs")
         x_c = torch.empty((g.n_c, 3), dtype=F64, device=dev)
         x_t = torch.empty((g.n_t, 3), dtype=F64, device=dev)
