@@ -204,3 +204,37 @@ def test_load_edges_reads_a_pickle_written_with_the_real_reference_class(tmp_pat
         assert type(out[k]["pose"]) is SE3
         assert np.array_equal(out[k]["pose"].R(), R) and np.array_equal(out[k]["pose"].t(), t)
         assert np.array_equal(out[k]["pose"].inv().R(), Ri)      # same float32 rounding as the reference container
+
+
+def test_accumulator_retires_a_detection_whose_newer_version_is_filtered_out():
+    """cam.py:263 merges per-image dictionaries: a re-detected key REPLACES the older detection; if the newer one
+    fails edge_filter the solver must not keep using the older one (the reference would filter the merged entry)."""
+    g = _graph(0.0)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    acc = vio.EdgeAccumulator(nr, nt, ef)
+    acc.add(edges)
+    n0 = len(acc)
+    k0 = next(iter(edges))
+    bad = dict(edges[k0], reprojected_err=1.0)           # newer detection of the same key, rejected by the filter
+    assert acc.add({k0: bad}) == 0 and len(acc) == n0 - 1
+    merged = dict(edges)
+    merged[k0] = bad
+    tab_ref = EdgeTable(merged, cons, nr, nt, ef)         # what the reference would solve on
+    tab = acc.table(cons)
+    assert tab.n_raw == tab_ref.n_raw == n0 - 1
+    # a later accepted detection of that key revives it
+    assert acc.add({k0: edges[k0]}) == 1 and len(acc) == n0
+
+
+def test_mixed_pose_dtypes_are_rejected():
+    """The float32 rounding of `k_r * pose.R()` (geometry.py:209-211) is mirrored per call, so a dictionary that
+    mixes float32 and float64 pose arrays is refused instead of silently promoted."""
+    g = _graph(0.0)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    k0 = next(iter(edges))
+    p = edges[k0]["pose"]
+    edges[k0] = dict(edges[k0], pose=SE3(R=p.R().astype(np.float32), t=p.t()))
+    with pytest.raises(ValueError):
+        EdgeTable(edges, cons, nr, nt, ef)
