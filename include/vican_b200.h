@@ -85,6 +85,11 @@ typedef struct vb_so3_options {
                              * reference's diagnostics (evals, eigengap = |lambda_4 / lambda_3|, bipgo.py:291, :336-339)
                              * and its early exit `max |lambda_1..5| <= 1e-6` (bipgo.py:283, :292), which can only
                              * fire on (nearly) disconnected graphs.  Costs one more eigen-solve per iteration. */
+    double  tol_early;      /* > 0: eigen-residual tolerance of the outer iterations that are followed by at least
+                             * `early_margin` more (inexact inner solves while the outer iteration is far from its fixed
+                             * point; the last `early_margin` iterations always use `tol`).  0: `tol` everywhere. */
+    int32_t early_margin;
+    int32_t reserved;
     void*   peer_ctx;       /* vb_peer_create context: the camera pass runs FUSED with its cross-rank sum over
                              * NVLink peer memory (allreduce / allreduce_ctx are then used for the few other
                              * reductions only and may point at vb_peer_allreduce); NULL: separate collective */

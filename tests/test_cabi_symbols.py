@@ -51,7 +51,7 @@ def test_version_and_status_strings(lib):
 def test_struct_layouts_match_header():
     from vican_b200._cabi import VbGraph, VbSo3Options, VbSo3Stats
     assert ctypes.sizeof(VbGraph) == 5 * 8 + 21 * 8
-    assert ctypes.sizeof(VbSo3Options) == 4 + 4 + 8 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(VbSo3Options) == 4 + 4 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(VbSo3Stats) == 6 * 4 + 3 * 8 + 3 * 8 + 8 + 64 * 4 + 8 + 8 + 4 + 4 + 4 + 4 + 64 * 5 * 8
 
 

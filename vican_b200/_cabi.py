@@ -46,7 +46,7 @@ class VbArrival(C.Structure):
 class VbSo3Options(C.Structure):
     _fields_ = [("maxiter", I32), ("max_inner", I32), ("tol", F64), ("allreduce", VP), ("allreduce_ctx", VP),
                 ("profile_events", I32), ("no_shortcut", I32), ("identity_start", I32), ("eval_gap", I32),
-                ("peer_ctx", VP)]
+                ("tol_early", F64), ("early_margin", I32), ("reserved", I32), ("peer_ctx", VP)]
 
 
 class VbSo3Stats(C.Structure):

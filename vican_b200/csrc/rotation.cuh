@@ -368,6 +368,7 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     double max_eval = 1.0;   // bipgo.py:280
     for (int outer = 0; outer < opt->maxiter; ++outer) {
         if (opt->eval_gap && max_eval <= 1e-6) { S->early_exit = 1; break; }   // bipgo.py:283-284
+        lp.tol = (opt->tol_early > 0.0 && opt->maxiter - outer > opt->early_margin) ? opt->tol_early : opt->tol;
         if (outer == 0) {
             if (opt->identity_start == 0) {   // one-hop spanning start (2 extra edge passes, see init_from_root_kernel)
                 fill_root_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, n_c);

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import os
 from typing import Optional
 
 import numpy as np
@@ -19,6 +20,8 @@ from ._cabi import VbGraph, VbSo3Options, VbSo3Stats, check
 
 F64 = torch.float64
 I32 = torch.int32
+# experiment switch (profiles/r2_inexact_inner.md): eigen tolerance of the early outer iterations; 0 = off
+_TOL_EARLY = float(os.environ.get("VICAN_B200_TOL_EARLY", "0"))
 SCHUR_MAX_CAMERAS = 4096      # dense direct translation solve: n_c^2 doubles (128 MB at the cap)
 
 
@@ -406,7 +409,8 @@ class RotationResult:
 
 def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner: int = 200,
                     comm: Optional[Comm] = None, profile_events: bool = False, shortcut: bool = True,
-                    spanning_start: bool = True, eval_gap: bool = False) -> RotationResult:
+                    spanning_start: bool = True, eval_gap: bool = False, tol_early: Optional[float] = None,
+                    early_margin: int = 4) -> RotationResult:
     """``shortcut=False`` forces the primal multiply through its two edge passes in every outer
     iteration (see ``vb_so3_stats.shortcut_outer``); ``spanning_start=False`` starts the first eigen-solve
     from identity blocks instead of the one-hop estimate around the gauge camera.  Both only change the
@@ -426,7 +430,8 @@ def solve_rotations(g: DeviceGraph, maxiter: int, tol: float = 1e-13, max_inner:
         fn, fctx = comm.reducer(lib, 9 * g.n_c) if comm is not None else (None, None)
         fused = comm.peer if (comm is not None and comm.peer is not None and 9 * g.n_c <= comm.peer_capacity) else None
         opt = VbSo3Options(int(maxiter), int(max_inner), float(tol), fn, fctx, 1 if profile_events else 0,
-                           0 if shortcut else 1, 0 if spanning_start else 1, 1 if eval_gap else 0, fused)
+                           0 if shortcut else 1, 0 if spanning_start else 1, 1 if eval_gap else 0,
+                           float(_TOL_EARLY if tol_early is None else tol_early), int(early_margin), 0, fused)
         stats = VbSo3Stats()
         rc = lib.vb_so3sync_run(C.byref(g.cgraph), C.byref(opt), _ptr(r_c), _ptr(r_t), _ptr(ws), wsb,
                                 C.byref(stats), _stream())
