@@ -86,8 +86,12 @@ typedef struct vb_so3_options {
                              * and its early exit `max |lambda_1..5| <= 1e-6` (bipgo.py:283, :292), which can only
                              * fire on (nearly) disconnected graphs.  Costs one more eigen-solve per iteration. */
     double  tol_early;      /* > 0: eigen-residual tolerance of the outer iterations that are followed by at least
-                             * `early_margin` more (inexact inner solves while the outer iteration is far from its fixed
-                             * point; the last `early_margin` iterations always use `tol`).  0: `tol` everywhere. */
+                             * `early_margin` more: inexact inner solves while the outer iteration is far from its
+                             * fixed point.  The last `early_margin` iterations always use `tol`; if the last two of
+                             * them do not accept their start block at the first step (the outer iteration had not
+                             * reached its fixed point to `tol` two iterations before the end, so the history still
+                             * matters), stats->inexact_unverified is set and the caller must repeat the run with
+                             * tol_early = 0.  0: `tol` everywhere. */
     int32_t early_margin;
     int32_t reserved;
     void*   peer_ctx;       /* vb_peer_create context: the camera pass runs FUSED with its cross-rank sum over
@@ -119,6 +123,8 @@ typedef struct vb_so3_stats {
     int32_t early_exit;     /* 1: the loop stopped before maxiter because max |lambda_1..5| <= 1e-6 (eval_gap only) */
     /* eval_gap: the five eigenvalues nearest zero of every outer iteration (bipgo.py:288-292), first 64 iterations */
     double  evals_hist[64][5];
+    int32_t inexact_unverified;   /* see vb_so3_options.tol_early */
+    int32_t reserved3;
 } vb_so3_stats;
 
 const char* vb_version(void);

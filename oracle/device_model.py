@@ -149,7 +149,8 @@ def lobpcg3(apply_L, prec, X0, tol, anorm, maxit=200, AX0=None):
     return X, th, napply, hist
 
 
-def so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-11, stats=None, shortcut=True, spanning_start=True):
+def so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-11, stats=None, shortcut=True, spanning_start=True,
+                  tol_early=0.0, early_margin=4):
     """Device algorithm for bipgo.py:243-348 (matrix-free, LOBPCG).  Same return
     convention as ``vican_oracle.so3sync``.
 
@@ -158,7 +159,10 @@ def so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-11, stats=None, shortc
     ``shortcut``: when an eigen-solve accepts its start block R (the previous r_c) without a single step, the
     eigenvectors are V = R C, so V_c V_0^-1 = R_c R_0^T is already a rotation and the primal multiply
     P Lambda_T P^T r_c equals Y R_0^T with Y = P Lambda_T P^T R computed for the eigen-residual: no edge passes
-    (csrc/rotation.cuh: so3sync_run).  ``stats.passes`` counts (time, camera) passes per outer iteration."""
+    (csrc/rotation.cuh: so3sync_run).  ``stats.passes`` counts (time, camera) passes per outer iteration.
+    ``tol_early`` > 0: inexact inner solves -- outer iterations followed by at least ``early_margin`` more stop their
+    eigen-solve at ``tol_early``; the last ``early_margin`` use ``tol`` (vb_so3_options.tol_early).
+    ``stats.applies[k] == 1`` means iteration k accepted its start block at the first step."""
     deg_t = np.zeros(n_t)
     np.add.at(deg_t, pt, a)
     deg_c = np.zeros(n_c)
@@ -202,7 +206,8 @@ def so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-11, stats=None, shortc
             npass[1] += 1                                   # camera pass only: the dual update emitted Wt
             Y = pass_cam(pc, pt, B, Wt_next, n_c)
         AX0 = (LamC @ X0b - Y).reshape(3 * n_c, 3)
-        V, th, napp, hist = lobpcg3(apply_L, prec, X0b.reshape(3 * n_c, 3), tol, anorm, AX0=AX0)
+        tol_k = tol_early if (tol_early > 0.0 and maxiter - outer > early_margin) else tol
+        V, th, napp, hist = lobpcg3(apply_L, prec, X0b.reshape(3 * n_c, 3), tol_k, anorm, AX0=AX0)
         if stats is not None:
             stats.applies.append(napp + 1)
             stats.resid.append(hist[-1] / anorm)

@@ -52,7 +52,7 @@ def test_struct_layouts_match_header():
     from vican_b200._cabi import VbGraph, VbSo3Options, VbSo3Stats
     assert ctypes.sizeof(VbGraph) == 5 * 8 + 21 * 8
     assert ctypes.sizeof(VbSo3Options) == 4 + 4 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(VbSo3Stats) == 6 * 4 + 3 * 8 + 3 * 8 + 8 + 64 * 4 + 8 + 8 + 4 + 4 + 4 + 4 + 64 * 5 * 8
+    assert ctypes.sizeof(VbSo3Stats) == 6 * 4 + 3 * 8 + 3 * 8 + 8 + 64 * 4 + 8 + 8 + 4 + 4 + 4 + 4 + 64 * 5 * 8 + 8
 
 
 def test_product_path_fails_loudly_without_gpu():

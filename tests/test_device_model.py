@@ -57,3 +57,21 @@ def test_shortcut_identity_holds_for_any_invertible_mix():
     ppwr = lambda X: dm.pass_cam(pc, pt, B, LamT @ dm.pass_time(pc, pt, B, X, n_t), n_c)  # noqa: E731
     Y = ppwr(R)
     assert np.abs(ppwr(rot) - Y @ R[0].T).max() < 1e-12 * np.abs(Y).max()
+
+
+@pytest.mark.parametrize("seed,shape,outl,maxiter", [(5, (12, 80, 4, 4, 2), 0.0, 10), (8, (15, 120, 6, 5, 3), 0.2, 12),
+                                                      (3, (20, 150, 4, 8, 2), 0.1, 10)])
+def test_inexact_early_eigen_solves_reach_the_same_fixed_point(seed, shape, outl, maxiter):
+    """vb_so3_options.tol_early: the eigen-solves of the early outer iterations stop at 1e-5 instead of 1e-13; the
+    last four are tight.  The primal-dual iteration contracts so strongly that the result equals the reference-
+    faithful oracle's (exact eigen-solves throughout) to 1e-9 rad, with far fewer applications of L -- and the
+    criterion the device uses to trust such a run (the last two tight iterations accept their start block at the
+    first step) holds."""
+    pc, pt, B, a, n_c, n_t = _pairs(seed, shape, outl)
+    r_c0, r_t0 = orc.so3sync(pc, pt, B, a, n_c, n_t, maxiter)
+    st_t, st_e = dm.LobpcgStats(), dm.LobpcgStats()
+    dm.so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-13, stats=st_t)
+    r_c, r_t = dm.so3sync_model(pc, pt, B, a, n_c, n_t, maxiter, tol=1e-13, stats=st_e, tol_early=1e-5, early_margin=4)
+    assert geodesic_rad(r_c, r_c0).max() < 1e-9 and geodesic_rad(r_t, r_t0).max() < 1e-9
+    assert st_e.applies[-1] == 1 and st_e.applies[-2] == 1
+    assert sum(st_e.applies) < sum(st_t.applies)

@@ -56,6 +56,7 @@ class VbSo3Stats(C.Structure):
         ("theta", F64 * 3), ("resid", F64 * 3), ("anorm", F64), ("inner_per_outer", I32 * 64),
         ("time_pass_ms", F64), ("cam_pass_ms", F64), ("time_pass_timed", I32), ("cam_pass_timed", I32),
         ("shortcut_outer", I32), ("early_exit", I32), ("evals_hist", (F64 * 5) * 64),
+        ("inexact_unverified", I32), ("reserved3", I32),
     ]
 
 

@@ -366,9 +366,13 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     static const bool lob_timing = getenv("VICAN_B200_LOBPCG_TIMING") != nullptr;   // diagnostics: stage times of every step
 
     double max_eval = 1.0;   // bipgo.py:280
+    int last_inner[2] = {0, 0};   // steps of the last two outer iterations (inexact-inner verification)
+    bool used_early = false;
     for (int outer = 0; outer < opt->maxiter; ++outer) {
         if (opt->eval_gap && max_eval <= 1e-6) { S->early_exit = 1; break; }   // bipgo.py:283-284
-        lp.tol = (opt->tol_early > 0.0 && opt->maxiter - outer > opt->early_margin) ? opt->tol_early : opt->tol;
+        const bool early = opt->tol_early > 0.0 && opt->maxiter - outer > opt->early_margin;
+        lp.tol = early ? opt->tol_early : opt->tol;
+        used_early = used_early || early;
         if (outer == 0) {
             if (opt->identity_start == 0) {   // one-hop spanning start (2 extra edge passes, see init_from_root_kernel)
                 fill_root_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.X, n_c);
@@ -451,6 +455,7 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
             }
         }
         if (outer < 64) S->inner_per_outer[outer] = inner;
+        last_inner[0] = last_inner[1]; last_inner[1] = inner;
         for (int j = 0; j < 3; ++j) { S->theta[j] = hs[SM_THETA + j]; S->resid[j] = hs[SM_RESN + j]; }
         S->anorm = hs[SM_ANORM];
 
@@ -520,6 +525,8 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         S->outer_done = outer + 1;
     }
     VB_CHECK(cudaStreamSynchronize(st));
+    // inexact early iterations are only trusted when the tight end-game shows the outer iteration AT its fixed point
+    if (used_early && !S->early_exit && !(last_inner[0] == 1 && last_inner[1] == 1)) S->inexact_unverified = 1;
     if (prof) {
         for (int slot = 0; slot < n_prof / 2; ++slot) {
             if (prof_kind[slot] < 0) continue;
