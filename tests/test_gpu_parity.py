@@ -464,3 +464,27 @@ def test_stalled_eigen_iteration_is_reported(cuda, monkeypatch):
     assert bipgo.last_info["eig_status"] == 2 and len(out) == 12 + 60
     with pytest.raises(solver.ConvergenceError):
         bipgo.bipartite_se3sync(edges, constraints, nr, nt, ef, 3, "conjugate_gradient", dtype=np.float64, strict=True)
+
+
+def test_inexact_early_eigen_solves_are_verified_or_repeated(cuda):
+    """vb_so3_options.tol_early (profiles/r2_inexact_inner.md): with the default margin the inexact run lands on the
+    all-tight result to rounding and on the oracle's; with a margin too short for the tight end-game to find the fixed
+    point the run is flagged (stats.inexact_unverified) and repeated all-tight: identical bits."""
+    from vican_b200.solver import solve_rotations
+    g = syn.make_camera_network(11, 40, 500, 24, 10, 4, outlier_frac=0.1, cube=True)
+    a = _arrays(g, False)                                   # outliers left in: slow outer convergence
+    dg = _device_graph(g, a)
+    maxiter = 10
+    tight = solve_rotations(dg, maxiter, tol_early=0.0)
+    dflt = solve_rotations(dg, maxiter)                     # tol_early = 1e-5, the last 4 iterations tight
+    assert not dflt.repeated_tight and dflt.stats.inexact_unverified == 0
+    assert sum(dflt.stats.inner_per_outer[:maxiter]) < sum(tight.stats.inner_per_outer[:maxiter])
+    assert geodesic_rad(dflt.r_c.cpu().numpy(), tight.r_c.cpu().numpy()).max() <= 1e-12
+    assert geodesic_rad(dflt.r_t.cpu().numpy(), tight.r_t.cpu().numpy()).max() <= 1e-12
+    pc, pt, B, av = _oracle_pairs(g, a)
+    r_c0, r_t0 = orc.so3sync(pc, pt, B, av, a["n_c"], a["n_t"], maxiter)
+    assert geodesic_rad(dflt.r_c.cpu().numpy().reshape(-1, 3, 3), r_c0).max() <= 1e-8
+    assert geodesic_rad(dflt.r_t.cpu().numpy().reshape(-1, 3, 3), r_t0).max() <= 1e-8
+    short = solve_rotations(dg, maxiter, tol_early=1e-2, early_margin=1)
+    assert short.repeated_tight
+    assert torch.equal(short.r_c, tight.r_c) and torch.equal(short.r_t, tight.r_t)
