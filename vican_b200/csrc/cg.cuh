@@ -470,8 +470,6 @@ struct CgMv {
     unsigned* ticket;
     int warps_cam;                    // warps [0, warps_cam) stream camera slices, the rest time slices
     int multi;                        // q_c is a partial sum over ranks: p_c . q_c is taken after the collective
-    int finalize;                     // 0: only write this launch's p.q partials (another launch finishes the sum)
-    int nb_cam_tab;                   // rows [0, nb_cam_tab) of the partial table belong to camera CTAs
 };
 
 constexpr int CG_MV_THREADS = 128;
@@ -628,19 +626,6 @@ __global__ void __launch_bounds__(CG_MV_THREADS, CG_MV_CTAS) cg_matvec_kernel(Cg
     // p . q: camera warps own whole CTAs [0, warps_cam / 4) (the host rounds warps_cam to CTAs), so the two parts
     // are summed separately and in a fixed order
     const double v[1] = {pq};
-    if (!a.finalize) {   // partials only (fixed order inside the CTA); the time-side launch finishes the sum
-        __shared__ double smp[CG_MV_WARPS];
-        const double ws = warp_sum(pq);
-        if ((threadIdx.x & 31) == 0) smp[threadIdx.x >> 5] = ws;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < CG_MV_WARPS; ++w) t += smp[w];
-            a.tab[blockIdx.x] = t;
-        }
-        return;
-    }
     if (cg_block_partial<1, CG_MV_WARPS>(v, a.tab, a.ticket)) {
         const int nb_cam = a.warps_cam / CG_MV_WARPS;
         const double pq_c = cg_table_sum<1, CG_MV_THREADS>(a.tab, 0, 0, nb_cam);
@@ -651,164 +636,6 @@ __global__ void __launch_bounds__(CG_MV_THREADS, CG_MV_CTAS) cg_matvec_kernel(Cg
             else a.sc[CG_ALPHA] = a.sc[CG_RHO] / (pq_c + pq_t);
             *a.ticket = 0u;
         }
-    }
-}
-
-// ---- time rows with the camera vector staged in shared memory -------------------------------------------------
-// The mat-vec is bound by the L1 data pipe: every gathered element costs one wavefront because every lane reads
-// another node.  The camera vector p_c is small (24 bytes per camera: 240 KB at 10 k cameras), so the TIME rows can
-// gather it from shared memory instead (bank conflicts of 8 random 24-byte rows: ~2.5 wavefronts per instruction
-// instead of 8).  It does not fit at once: the cameras are processed in H ascending ranges; a pass stages one range
-// and every warp streams its slices' chunks again, handling the entries of that range.  Entries of a row ascend
-// with the camera index, so the passes continue the row's sequential chain exactly where the previous one stopped
-// (the partial sum waits in q_t): the arithmetic is bit for bit that of cg_stream_rows.
-constexpr int CG_TS_THREADS = 512;
-constexpr int CG_TS_WARPS = CG_TS_THREADS / 32;
-constexpr int CG_TS_MAX_SMEM = 200 * 1024;
-
-__device__ __forceinline__ void cg_stream_time_smem(const SellSide& S, int64_t s0, int64_t s1, const double* sp, int lo, int hi,
-                                                    bool first_pass, bool last_pass, double& pq) {
-    if (s0 >= s1) return;
-    const int lane = threadIdx.x & 31, j = lane >> 2, d = lane & 3;
-    const int dd = d < 3 ? d : 0;
-    const int cbeg = __ldg(S.ptr + s0), cend = __ldg(S.ptr + s1);
-    int4 idx_nx[CG_U]; double w_nx[CG_U][4];
-    auto loadA = [&](int q0) {
-#pragma unroll
-        for (int u = 0; u < CG_U; ++u) {
-            idx_nx[u] = make_int4(-1, -1, -1, -1);
-            w_nx[u][0] = w_nx[u][1] = w_nx[u][2] = w_nx[u][3] = 0.0;
-            if (q0 + u < cend) {
-                const int64_t base = 32 * (int64_t)(q0 + u) + 4 * j;
-                asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(idx_nx[u].x), "=r"(idx_nx[u].y), "=r"(idx_nx[u].z), "=r"(idx_nx[u].w) : "l"(S.idx + base));
-                asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                             : "=d"(w_nx[u][0]), "=d"(w_nx[u][1]), "=d"(w_nx[u][2]), "=d"(w_nx[u][3]) : "l"(S.w + base));
-            }
-        }
-    };
-    int64_t slice = s0;
-    int slice_end = __ldg(S.ptr + s0 + 1);
-    double acc = 0.0, diag = 0.0, pself = 0.0, n_pself = 0.0, n_dg = 0.0, n_acc = 0.0;
-    int ins = 0x7fffffff, n_ins = 0x7fffffff, k = 0;
-    bool pending = false, active = false;
-    auto fetch_row = [&](int64_t sl) {
-        const int64_t row = SELL_ROWS * sl + j;
-        n_pself = 0.0; n_dg = 0.0; n_ins = S.ins_default; n_acc = 0.0;
-        if (sl < s1 && d < 3 && row < S.n_rows) {
-            n_pself = S.p_self[4 * row + d];
-            if (S.add_diag) { n_dg = S.dg[row]; if (S.ins) n_ins = S.ins[row]; }
-            if (!first_pass) n_acc = S.q[3 * row + d];     // the chain so far (written by the previous pass)
-        }
-    };
-    auto start_row = [&](int64_t sl) {
-        const int64_t row = SELL_ROWS * sl + j;
-        active = (d < 3) && (row < S.n_rows);
-        acc = n_acc; k = 0; pself = n_pself; pending = false; ins = 0x7fffffff;
-        if (active && S.add_diag) { diag = __dmul_rn(n_dg, pself); pending = true; ins = n_ins; }
-        fetch_row(sl + 1);
-    };
-    auto finish_row = [&](int64_t sl) {
-        if (!active) return;
-        const int64_t row = SELL_ROWS * sl + j;
-        if (last_pass && pending) acc = __dadd_rn(acc, diag);
-        S.q[3 * row + d] = acc;
-        if (last_pass) pq += pself * acc;
-    };
-    fetch_row(s0);
-    start_row(s0);
-    loadA(cbeg);
-    for (int q0 = cbeg; q0 < cend; q0 += CG_U) {
-        int id[CG_U][4]; double pr[CG_U][4];
-#pragma unroll
-        for (int u = 0; u < CG_U; ++u) {
-            id[u][0] = idx_nx[u].x; id[u][1] = idx_nx[u].y; id[u][2] = idx_nx[u].z; id[u][3] = idx_nx[u].w;
-#pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {
-                const int c = id[u][sub];
-                double pv = 0.0;
-                if (c >= lo && c < hi) pv = sp[3 * (c - lo) + dd];
-                pr[u][sub] = __dmul_rn(w_nx[u][sub], pv);
-            }
-        }
-        loadA(q0 + CG_U);
-#pragma unroll
-        for (int u = 0; u < CG_U; ++u) {
-            const int cq = q0 + u;
-            if (cq < cend) {        // warp-uniform
-                while (cq == slice_end) {
-                    finish_row(slice);
-                    ++slice;
-                    slice_end = __ldg(S.ptr + slice + 1);
-                    start_row(slice);
-                }
-#pragma unroll
-                for (int sub = 0; sub < 4; ++sub) {
-                    const int c = id[u][sub];
-                    if (c >= 0 && c < hi) {                  // entries of later ranges wait for their pass
-                        if (pending && k == ins) {           // the diagonal's sorted position
-                            if (c >= lo) acc = __dadd_rn(acc, diag);   // (an earlier pass added it when c < lo)
-                            pending = false;
-                        }
-                        if (c >= lo) acc = __dsub_rn(acc, pr[u][sub]);
-                        ++k;
-                    }
-                }
-            }
-        }
-    }
-    for (;;) {
-        finish_row(slice);
-        if (++slice >= s1) break;
-        start_row(slice);
-    }
-}
-
-__global__ void __launch_bounds__(CG_TS_THREADS, 1) cg_matvec_time_smem_kernel(CgMv a, int n_ranges, int range) {
-    if (a.sc[CG_DONE] != 0.0) return;
-    extern __shared__ __align__(16) double cg_sp[];
-    const int wv = threadIdx.x >> 5;
-    const int64_t gw = (int64_t)blockIdx.x * CG_TS_WARPS + wv;
-    const int64_t nw = (int64_t)gridDim.x * CG_TS_WARPS;
-    const int64_t per = (a.time.n_slices + nw - 1) / nw;
-    const int64_t s0 = gw * per, s1 = (s0 + per < a.time.n_slices) ? s0 + per : a.time.n_slices;
-    const int n_c = (int)a.cam.n_rows;
-    double pq = 0.0;
-    for (int h = 0; h < n_ranges; ++h) {
-        const int lo = h * range, hi = (lo + range < n_c) ? lo + range : n_c;
-        __syncthreads();                                   // everyone is done with the previous range
-        for (int i = threadIdx.x; i < 3 * (hi - lo); i += CG_TS_THREADS) {
-            const int c = i / 3;
-            cg_sp[i] = a.time.p_other[4 * (int64_t)(lo + c) + (i - 3 * c)];
-        }
-        __syncthreads();
-        cg_stream_time_smem(a.time, s0, s1, cg_sp, lo, hi, h == 0, h == n_ranges - 1, pq);
-    }
-    // p . q: the camera launch left its per-CTA partials in rows [0, nb_cam_tab); this launch adds its own and finishes
-    __shared__ double smp[CG_TS_WARPS];
-    __shared__ bool last;
-    const double ws = warp_sum(pq);
-    if ((threadIdx.x & 31) == 0) smp[threadIdx.x >> 5] = ws;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < CG_TS_WARPS; ++w) t += smp[w];
-        a.tab[a.nb_cam_tab + blockIdx.x] = t;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const double pq_c = cg_table_sum<1, CG_TS_THREADS>(a.tab, 0, 0, a.nb_cam_tab);
-    const double pq_t = cg_table_sum<1, CG_TS_THREADS>(a.tab, 0, a.nb_cam_tab, a.nb_cam_tab + (int)gridDim.x);
-    if (threadIdx.x == 0) {
-        a.sc[CG_PQ_C] = pq_c; a.sc[CG_PQ_T] = pq_t;
-        if (a.multi) a.cam.q[3 * a.cam.n_rows] = pq_t;
-        else a.sc[CG_ALPHA] = a.sc[CG_RHO] / (pq_c + pq_t);
-        *a.ticket = 0u;
     }
 }
 
@@ -875,42 +702,7 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     if (time_ctas < 1 && ns_t > 0) time_ctas = 1;
     if (cam_ctas + time_ctas > CG_MAX_BLOCKS) return VB_STATUS_BAD_ARGUMENT;
     mv.warps_cam = (int)cam_ctas * CG_MV_WARPS;
-    mv.finalize = 1;
-    mv.nb_cam_tab = (int)cam_ctas;
     const int mv_grid = (int)(cam_ctas + time_ctas);
-    // Time rows with the camera vector staged in shared memory (cg_matvec_time_smem_kernel): the camera rows get a
-    // launch of their own (every warp a camera slice), the time rows one CTA of 16 warps per SM and H passes over
-    // ascending camera ranges of at most CG_TS_MAX_SMEM bytes.  VICAN_B200_CG_SMEM=0 keeps the single launch.
-    static const bool use_smem = !(getenv("VICAN_B200_CG_SMEM") && atoi(getenv("VICAN_B200_CG_SMEM")) == 0);
-    const int n_ranges = (int)((24 * n_c + CG_TS_MAX_SMEM - 1) / CG_TS_MAX_SMEM);
-    const int range = (int)((n_c + n_ranges - 1) / n_ranges);
-    const bool smem_path = use_smem && ns_t > 0 && n_ranges <= 8;
-    CgMv mv_cam = mv, mv_time = mv;
-    int cam_grid = 0, ts_grid = 0;
-    if (smem_path) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            VB_CHECK(cudaFuncSetAttribute(cg_matvec_time_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_TS_MAX_SMEM));
-            attr_set = true;
-        }
-        int64_t cc = (ns_c + CG_MV_WARPS - 1) / CG_MV_WARPS;
-        if (cc > cap) cc = cap;
-        cam_grid = (int)cc;
-        mv_cam.warps_cam = cam_grid * CG_MV_WARPS; mv_cam.finalize = 0; mv_cam.nb_cam_tab = cam_grid;
-        int64_t tg = (ns_t + CG_TS_WARPS - 1) / CG_TS_WARPS;
-        if (tg > sm_count()) tg = sm_count();
-        ts_grid = (int)tg;
-        mv_time.nb_cam_tab = cam_grid;
-        if (cam_grid + ts_grid > CG_MAX_BLOCKS) return VB_STATUS_BAD_ARGUMENT;
-    }
-    auto launch_matvec = [&]() {
-        if (smem_path) {
-            cg_matvec_kernel<false><<<cam_grid, CG_MV_THREADS, 0, st>>>(mv_cam);
-            cg_matvec_time_smem_kernel<<<ts_grid, CG_TS_THREADS, (size_t)24 * range, st>>>(mv_time, n_ranges, range);
-        } else {
-            cg_matvec_kernel<false><<<mv_grid, CG_MV_THREADS, 0, st>>>(mv);
-        }
-    };
 
     if (unk_c != nullptr && unk_t != nullptr) {
         const int capw = sm_count() * 8;
@@ -918,8 +710,6 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
         cg_ins_kernel<<<gc < capw ? gc : capw, CG_THREADS, 0, st>>>(g->sc_ptr, g->sc_idx, n_c, ns_c, unk_c, unk_t, w.ins_c);
         if (ns_t > 0) cg_ins_kernel<<<gt < capw ? gt : capw, CG_THREADS, 0, st>>>(g->st_ptr, g->st_idx, n_t, ns_t, unk_t, unk_c, w.ins_t);
         mv.cam.ins = w.ins_c; mv.time.ins = w.ins_t;
-        mv_cam.cam.ins = w.ins_c; mv_cam.time.ins = w.ins_t;
-        mv_time.cam.ins = w.ins_c; mv_time.time.ins = w.ins_t;
     }
     {   // weighted degrees = diagonal of J^T J: the same sequential row sums, over the weights
         CgMv dm = mv;
@@ -958,7 +748,7 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     for (int b = 1;; ++b) {
         for (int i = 0; i < batch && enq < maxiter; ++i, ++enq) {
             cg_dir_kernel<<<vgrid, CG_THREADS, 0, st>>>(v);
-            launch_matvec();
+            cg_matvec_kernel<false><<<mv_grid, CG_MV_THREADS, 0, st>>>(mv);
             if (multi) {
                 int rc = allreduce(actx, w.q_c, 3 * n_c + 8, (void*)st);
                 if (rc) return rc;
@@ -986,7 +776,7 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     VB_CHECK(cudaStreamSynchronize(st));   // the speculative tail (no-ops) must not outlive the workspace
     // executed launches: degrees, init, 3 per executed iteration (+ the scalar kernels of a sharded run);
     // iterations enqueued after convergence return at their first instruction and are not counted
-    count_launches(2 + (unk_c != nullptr ? 2 : 0) + (multi ? 1 : 0) + (long long)hs[CG_ITERS] * ((multi ? 5 : 3) + (smem_path ? 1 : 0)));
+    count_launches(2 + (unk_c != nullptr ? 2 : 0) + (multi ? 1 : 0) + (long long)hs[CG_ITERS] * (multi ? 5 : 3));
     if (h_iters) *h_iters = (int32_t)hs[CG_ITERS];
     return status;
 }
