@@ -37,6 +37,14 @@ if rank == 0:
             gaps.append((s - last_end, e.name[:50]))
         busy += max(0.0, en - max(s, last_end)); last_end = max(last_end, en)
         a = agg.setdefault(e.name[:60], [0, 0.0]); a[0] += 1; a[1] += (en - s)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/timeline_%dgpu.csv" % world, "w") as f:
+        f.write("start_us,dur_us,gap_before_us,name\n")
+        prev = t0
+        for e in evs:
+            f.write("%.1f,%.1f,%.1f,%s\n" % (e.time_range.start - t0, e.time_range.end - e.time_range.start,
+                                             e.time_range.start - prev, e.name[:70].replace(",", ";")))
+            prev = max(prev, e.time_range.end)
     print("world %d: span %.2f ms, busy %.2f ms, idle %.2f ms, kernels %d, phases %s" % (world, (t1 - t0) / 1e3, busy / 1e3, (t1 - t0 - busy) / 1e3, len(evs), r.phase_ms))
     gaps.sort(reverse=True)
     print("largest gaps (us, next kernel):", [(round(g, 1), n) for g, n in gaps[:14]])

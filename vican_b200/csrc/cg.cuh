@@ -30,6 +30,7 @@
 #include "../../include/vican_b200.h"
 #include "common.cuh"
 #include "passes.cuh"
+#include "peer.cuh"
 #include "rotation.cuh"
 
 namespace vb {
@@ -244,6 +245,8 @@ inline int sell_fill(const vb_graph* g, const int32_t* st_ptr, int32_t* st_idx, 
 // ------------------------------------------------------------------------------------- CG
 enum { CG_RHO = 0, CG_BETA, CG_ALPHA, CG_DONE, CG_ITERS, CG_ATOL, CG_BN2, CG_RZ_C, CG_RZ_T, CG_RR_C, CG_RR_T, CG_PQ_C,
        CG_PQ_T, CG_NSCAL = 16 };
+constexpr int CG_PQ_SLOT = 4;   // sharded runs: q_c[3 n_c + CG_PQ_SLOT .. + 1] carry the two halves of p . q through the collective
+                                // (slots 0..2 behind the camera vector are the r.r / r.z pack)
 
 struct CgWork {
     double *r_c, *p_c, *q_c, *dg_c;   // p padded [n][4]; q_c has 8 pack slots behind it
@@ -411,7 +414,9 @@ __global__ void __launch_bounds__(CG_THREADS) cg_update_kernel(CgVec a) {
     const bool ok = cg_node(a, i, cam);
     double v[2] = {0.0, 0.0};
     if (ok) {
-        const double alpha = a.sc[CG_ALPHA];
+        // sharded: both halves of p . q arrive summed over ranks behind the camera vector (CG_PQ_SLOT)
+        const double alpha = a.multi ? a.sc[CG_RHO] / (a.q_c[3 * a.n_c + CG_PQ_SLOT + 1] + a.q_c[3 * a.n_c + CG_PQ_SLOT])
+                                     : a.sc[CG_ALPHA];
         double* x = cam ? a.x_c : a.x_t; double* r = cam ? a.r_c : a.r_t;
         const double* p = cam ? a.p_c : a.p_t; const double* q = cam ? a.q_c : a.q_t;
         const double d = a.jacobi ? 1.0 / (cam ? a.dg_c : a.dg_t)[i] : 1.0;
@@ -433,26 +438,6 @@ __global__ void cg_top_multi_kernel(double* sc, const double* pack, double rtol,
     cg_top(sc, rtol, first);
 }
 
-// multi-rank: p_c . q_c after the cross-rank sum of q_c (one block, fixed order), then alpha
-__global__ void __launch_bounds__(1024) cg_alpha_multi_kernel(const double* __restrict__ p_c, const double* __restrict__ q_c, int64_t n_c,
-                                                             double* sc) {
-    if (sc[CG_DONE] != 0.0) return;
-    __shared__ double sm[32];
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < n_c; i += 1024)
-        s += p_c[4 * i] * q_c[3 * i] + p_c[4 * i + 1] * q_c[3 * i + 1] + p_c[4 * i + 2] * q_c[3 * i + 2];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 32; ++w) t += sm[w];
-        sc[CG_PQ_C] = t;
-        sc[CG_PQ_T] = q_c[3 * n_c];   // summed over ranks with the accumulator
-        sc[CG_ALPHA] = sc[CG_RHO] / (sc[CG_PQ_C] + sc[CG_PQ_T]);
-    }
-}
-
 // ------------------------------------------------------------------------------- mat-vec
 // One side of the bipartite Laplacian in the sliced-ELL layout, as seen by the mat-vec.
 struct SellSide {
@@ -469,7 +454,7 @@ struct CgMv {
     double *sc, *tab;
     unsigned* ticket;
     int warps_cam;                    // warps [0, warps_cam) stream camera slices, the rest time slices
-    int multi;                        // q_c is a partial sum over ranks: p_c . q_c is taken after the collective
+    int multi;                        // q_c is a partial sum over ranks: the halves of p . q ride with it (CG_PQ_SLOT)
 };
 
 constexpr int CG_MV_THREADS = 128;
@@ -497,7 +482,7 @@ __device__ __forceinline__ double ld_stream_d(const double* p) {
 // the SM cover the gather latency.  L1 wavefronts per chunk: 32 (gathers) + 3, the floor for this access pattern.
 // Slice boundaries inside a step are handled in the chain loop (rows finish, the next slice's rows start).
 template <bool DIAGMODE>
-__device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, int64_t s1, bool count_pq, double& pq) {
+__device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, int64_t s1, double& pq) {
     if (s0 >= s1) return;
     const int lane = threadIdx.x & 31, j = lane >> 2, d = lane & 3;
     const int cbeg = __ldg(S.ptr + s0), cend = __ldg(S.ptr + s1);
@@ -544,7 +529,7 @@ __device__ __forceinline__ void cg_stream_rows(const SellSide& S, int64_t s0, in
         if (DIAGMODE) { if (d == 0) S.q[row] = acc; }
         else {
             S.q[3 * row + d] = acc;
-            if (count_pq) pq += pself * acc;
+            pq += pself * acc;
         }
     };
     fetch_row(s0);
@@ -615,12 +600,12 @@ __global__ void __launch_bounds__(CG_MV_THREADS, CG_MV_CTAS) cg_matvec_kernel(Cg
     if (gw < a.warps_cam) {
         const int64_t per = (a.cam.n_slices + a.warps_cam - 1) / a.warps_cam;
         const int64_t s0 = gw * per, s1 = (s0 + per < a.cam.n_slices) ? s0 + per : a.cam.n_slices;
-        cg_stream_rows<DIAGMODE>(a.cam, s0, s1, !a.multi, pq);
+        cg_stream_rows<DIAGMODE>(a.cam, s0, s1, pq);
     } else {
         const int64_t wt = nw - a.warps_cam, me = gw - a.warps_cam;
         const int64_t per = (a.time.n_slices + wt - 1) / (wt > 0 ? wt : 1);
         const int64_t s0 = me * per, s1 = (s0 + per < a.time.n_slices) ? s0 + per : a.time.n_slices;
-        cg_stream_rows<DIAGMODE>(a.time, s0, s1, true, pq);
+        cg_stream_rows<DIAGMODE>(a.time, s0, s1, pq);
     }
     if (DIAGMODE) return;
     // p . q: camera warps own whole CTAs [0, warps_cam / 4) (the host rounds warps_cam to CTAs), so the two parts
@@ -632,8 +617,13 @@ __global__ void __launch_bounds__(CG_MV_THREADS, CG_MV_CTAS) cg_matvec_kernel(Cg
         const double pq_t = cg_table_sum<1, CG_MV_THREADS>(a.tab, 0, nb_cam, gridDim.x);
         if (threadIdx.x == 0) {
             a.sc[CG_PQ_C] = pq_c; a.sc[CG_PQ_T] = pq_t;
-            if (a.multi) a.cam.q[3 * a.cam.n_rows] = pq_t;     // rides with the camera accumulator through the collective
-            else a.sc[CG_ALPHA] = a.sc[CG_RHO] / (pq_c + pq_t);
+            if (a.multi) {
+                // q_c is this rank's partial sum and the dot product is linear in it: both halves ride with the
+                // camera vector through the collective, cg_update_kernel divides
+                a.cam.q[3 * a.cam.n_rows + CG_PQ_SLOT] = pq_t; a.cam.q[3 * a.cam.n_rows + CG_PQ_SLOT + 1] = pq_c;
+            } else {
+                a.sc[CG_ALPHA] = a.sc[CG_RHO] / (pq_c + pq_t);
+            }
             *a.ticket = 0u;
         }
     }
@@ -735,6 +725,8 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     // read, so the GPU never idles on the host; iterations enqueued after convergence return at once.
     PinnedStatus& ps = pinned_state();
     int status = VB_STATUS_NOT_CONVERGED;
+    // peer-memory collectives skip themselves once the done flag is up (identical on all ranks)
+    PeerSkipScope skip_scope(allreduce == (vb_allreduce_fn)&vb_peer_allreduce ? (PeerCtx*)actx : nullptr, w.sc + CG_DONE);
     const int batch = 4;
     int64_t enq = 0;
     double* hs = ps.h;
@@ -752,7 +744,6 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
             if (multi) {
                 int rc = allreduce(actx, w.q_c, 3 * n_c + 8, (void*)st);
                 if (rc) return rc;
-                cg_alpha_multi_kernel<<<1, 1024, 0, st>>>(w.p_c, w.q_c, n_c, w.sc);
             }
             cg_update_kernel<<<vgrid, CG_THREADS, 0, st>>>(v);
             VB_KERNEL_CHECK();
@@ -776,7 +767,7 @@ inline int trans_cg(const vb_graph* g, const double* rhs_c, const double* rhs_t,
     VB_CHECK(cudaStreamSynchronize(st));   // the speculative tail (no-ops) must not outlive the workspace
     // executed launches: degrees, init, 3 per executed iteration (+ the scalar kernels of a sharded run);
     // iterations enqueued after convergence return at their first instruction and are not counted
-    count_launches(2 + (unk_c != nullptr ? 2 : 0) + (multi ? 1 : 0) + (long long)hs[CG_ITERS] * (multi ? 5 : 3));
+    count_launches(2 + (unk_c != nullptr ? 2 : 0) + (multi ? 1 : 0) + (long long)hs[CG_ITERS] * (multi ? 4 : 3));
     if (h_iters) *h_iters = (int32_t)hs[CG_ITERS];
     return status;
 }

@@ -58,6 +58,19 @@ struct PeerCtx {
     void* base = nullptr;
     void* opened[PEER_MAX] = {nullptr};
     size_t bytes = 0;
+    const double* skip = nullptr;   // see PeerSkipScope
+};
+
+// While alive, the generic all-reduces of this context return at their first instruction when *flag != 0.  The flag
+// must hold the same value on every rank at every call (it does for the CG's done flag: it is computed from sums
+// that are bitwise identical on all ranks), so either all ranks exchange or none does and the epochs stay in step.
+// Iterations a host loop enqueued past convergence then cost a launch, not an NVLink round trip.
+struct PeerSkipScope {
+    PeerCtx* ctx;
+    PeerSkipScope(PeerCtx* c, const double* flag) : ctx(c) { if (ctx) ctx->skip = flag; }
+    ~PeerSkipScope() { if (ctx) ctx->skip = nullptr; }
+    PeerSkipScope(const PeerSkipScope&) = delete;
+    PeerSkipScope& operator=(const PeerSkipScope&) = delete;
 };
 
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
@@ -156,7 +169,9 @@ __device__ __forceinline__ void peer_reduce(const PeerDev& pd, unsigned long lon
 }
 
 // generic in-place all-reduce of a small vector (count <= cap)
-__global__ void __launch_bounds__(PEER_AR_THREADS) peer_allreduce_kernel(PeerDev pd, double* __restrict__ data, long long count) {
+__global__ void __launch_bounds__(PEER_AR_THREADS) peer_allreduce_kernel(PeerDev pd, double* __restrict__ data, long long count,
+                                                                             const double* __restrict__ skip) {
+    if (skip != nullptr && *skip != 0.0) return;
     const unsigned long long epoch = pd.ctrl[pd.rank]->epoch + 1ull;   // advanced by the previous call's last CTA
     double* mine = pd.buf[pd.rank] + (long long)(epoch & 1ull) * pd.cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -172,7 +187,8 @@ inline int launch_peer_allreduce(PeerCtx* ctx, double* data, int64_t count, cuda
     if (grid < 16) grid = 16;             // even a 3-scalar call may have to clear a camera accumulator (see peer_reduce)
     if (grid > PEER_AR_CTAS) grid = PEER_AR_CTAS;
     long long cnt = count;
-    void* args[] = {(void*)&ctx->dev, (void*)&data, (void*)&cnt};
+    const double* skip = ctx->skip;
+    void* args[] = {(void*)&ctx->dev, (void*)&data, (void*)&cnt, (void*)&skip};
     VB_CHECK(cudaLaunchCooperativeKernel((void*)peer_allreduce_kernel, dim3(grid), dim3(PEER_AR_THREADS), args, 0, st));
     return 0;
 }

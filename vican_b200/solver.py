@@ -551,6 +551,7 @@ def solve_translations(g: DeviceGraph, rot: RotationResult, t_cm, marker_q, lsqr
 
 
 _PINNED_OUT = {}
+_DOWNLOAD_STREAM = {}
 
 
 def _to_pinned_host(name: str, t: torch.Tensor, reuse: bool) -> torch.Tensor:
@@ -605,13 +606,25 @@ def solve_arrays(cam, time, marker, R, t, k_r, k_t, markerC, marker_q, n_c: int,
     ev[1].record()
     rot = solve_rotations(g, maxiter, tol=tol, comm=comm, profile_events=profile_events)
     ev[2].record()
+    Rw_c, Rw_t = rot.world_rotations()
+    if to_host:
+        # the rotations (72 of the 96 result bytes per node) go home on a side stream under the translation stage
+        cur = torch.cuda.current_stream(g.device)
+        dl = _DOWNLOAD_STREAM.get(g.device)
+        if dl is None:
+            dl = _DOWNLOAD_STREAM[g.device] = torch.cuda.Stream(device=g.device)
+        dl.wait_stream(cur)
+        with torch.cuda.stream(dl):
+            host_R = [_to_pinned_host(n, v, reuse_host_buffers) for n, v in (("Rw_c", Rw_c), ("Rw_t", Rw_t))]
+        for v in (Rw_c, Rw_t):
+            v.record_stream(dl)
     tr = solve_translations(g, rot, upload.get("t") if upload is not None else t, marker_q, lsqr_solver,
                             mode=mode, comm=comm)
-    Rw_c, Rw_t = rot.world_rotations()
     x_c, x_t = tr.x_c, tr.x_t
     if to_host:
-        Rw_c, Rw_t, x_c, x_t = (_to_pinned_host(n, v, reuse_host_buffers) for n, v in
-                                (("Rw_c", Rw_c), ("Rw_t", Rw_t), ("x_c", x_c), ("x_t", x_t)))
+        x_c, x_t = (_to_pinned_host(n, v, reuse_host_buffers) for n, v in (("x_c", x_c), ("x_t", x_t)))
+        cur.wait_stream(dl)
+        Rw_c, Rw_t = host_R
     ev[3].record()
     torch.cuda.synchronize()
     if comm is not None and comm.peer is not None:
