@@ -238,3 +238,86 @@ def test_mixed_pose_dtypes_are_rejected():
     edges[k0] = dict(edges[k0], pose=SE3(R=p.R().astype(np.float32), t=p.t()))
     with pytest.raises(ValueError):
         EdgeTable(edges, cons, nr, nt, ef)
+
+
+# ---------------------------------------------------------------------------------------------
+# the C walk of the dictionary (vican_b200/csrc/flatten.c) against the list-comprehension statement
+# ---------------------------------------------------------------------------------------------
+
+def _both(edges, cons, nr, nt, ef, monkeypatch):
+    from vican_b200 import bipgo
+    assert bipgo._vb_flatten is not None, "vican_b200/_vb_flatten*.so not built (run __graft_entry__.build())"
+    monkeypatch.setenv("VICAN_B200_PY_FLATTEN", "0")
+    a = EdgeTable(edges, cons, nr, nt, ef)
+    monkeypatch.setenv("VICAN_B200_PY_FLATTEN", "1")
+    b = EdgeTable(edges, cons, nr, nt, ef)
+    return a, b
+
+
+def test_c_flatten_equals_python_flatten(monkeypatch):
+    g = _graph(0.3)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    _same(*_both(edges, cons, nr, nt, ef, monkeypatch))
+    # weights of other numeric types: Python int, numpy scalars, 0-d arrays
+    _same(*_both(edges, cons, lambda e: 2, lambda e: np.float32(0.5), lambda e: np.bool_(True), monkeypatch))
+    _same(*_both(edges, cons, lambda e: np.float64(1.5), lambda e: np.asarray(0.25), lambda e: 1, monkeypatch))
+
+
+def test_c_flatten_float32_poses_and_column_translations(monkeypatch):
+    g = _graph(0.0)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    e32 = {k: dict(v, pose=SE3(R=v["pose"].R().astype(np.float32), t=v["pose"].t().astype(np.float32).reshape(3, 1)))
+           for k, v in edges.items()}
+    a, b = _both(e32, cons, nr, nt, ef, monkeypatch)
+    _same(a, b)
+    assert a.round_kr_f32 and a.R.dtype == np.float64
+    # numpy-scalar weights keep the product in float64 (bipgo.py:212 under numpy's promotion rules)
+    a, b = _both(e32, cons, lambda e: np.float64(1.0), nt, ef, monkeypatch)
+    assert not a.round_kr_f32 and not b.round_kr_f32
+    # non-contiguous views and other dtypes go through numpy's conversion
+    big = np.zeros((6, 6))
+    odd = {}
+    for k, v in edges.items():
+        big = np.zeros((6, 6))
+        big[::2, ::2] = v["pose"].R()
+        odd[k] = dict(v, pose=SE3(R=big[::2, ::2], t=v["pose"].t()))
+    a = EdgeTable(odd, cons, nr, nt, ef)
+    c = EdgeTable(edges, cons, nr, nt, ef)
+    _same(a, c)
+
+
+def test_c_flatten_errors_match(monkeypatch):
+    g = _graph(0.0)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    keys = list(edges.keys())
+    mixed = dict(edges)
+    mixed[keys[3]] = dict(edges[keys[3]], pose=SE3(R=edges[keys[3]]["pose"].R().astype(np.float32),
+                                                   t=edges[keys[3]]["pose"].t()))
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VICAN_B200_PY_FLATTEN", flag)
+        with pytest.raises(ValueError, match="mix float32 and float64"):
+            EdgeTable(mixed, cons, nr, nt, ef)
+        with pytest.raises(ValueError, match="no edge passes"):
+            EdgeTable(edges, cons, nr, nt, lambda e: False)
+        with pytest.raises(ZeroDivisionError):
+            EdgeTable(edges, cons, lambda e: 1 / 0, nt, ef)
+        with pytest.raises(KeyError):
+            EdgeTable(edges, {k: v for k, v in cons.items() if k != "1"}, nr, nt, ef)
+        with pytest.raises(KeyError):                                    # detection without a pose
+            EdgeTable({keys[0]: {"corners": edges[keys[0]]["corners"], "reprojected_err": 0.0}}, cons, nr, nt, ef)
+
+
+def test_c_flatten_call_counts_and_order(monkeypatch):
+    g = _graph(0.3)
+    edges, cons = syn.to_edge_dict(g, SE3)
+    _, _, ef0 = syn.default_callables()
+    seen = {"f": [], "r": [], "t": []}
+    monkeypatch.setenv("VICAN_B200_PY_FLATTEN", "0")
+    EdgeTable(edges, cons, lambda e: seen["r"].append(id(e)) or 1.0, lambda e: seen["t"].append(id(e)) or 1.0,
+              lambda e: seen["f"].append(id(e)) or ef0(e))
+    kept = [id(v) for v in edges.values() if ef0(v)]
+    assert seen["f"] == [id(v) for v in edges.values()]                  # insertion order, once each
+    assert seen["r"] == kept and seen["t"] == kept

@@ -13,6 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libvican_b200.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
+FLATTEN_SRC = os.path.join(_HERE, "csrc", "flatten.c")
 
 _lock = threading.Lock()
 _lib = None
@@ -130,7 +131,24 @@ def build(verbose: bool = False) -> str:
         raise RuntimeError("building libvican_b200.so failed:\n" + out.stdout + out.stderr)
     if verbose:
         print(out.stdout)
+    build_flatten()
     return SO_PATH
+
+
+def flatten_so_path() -> str:
+    import sysconfig
+    return os.path.join(_HERE, "_vb_flatten" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_flatten() -> str:
+    """Compile the host-side dictionary flatten (CPython extension, csrc/flatten.c) in-tree with gcc."""
+    import sysconfig
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-Wall", "-I", sysconfig.get_paths()["include"], FLATTEN_SRC,
+           "-o", flatten_so_path()]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building _vb_flatten failed:\n" + out.stdout + out.stderr)
+    return flatten_so_path()
 
 
 def load_library():

@@ -11,6 +11,7 @@ per detection, while the dictionary is flattened into arrays; nothing else does.
 from __future__ import annotations
 
 import gc
+import os
 import time as _time
 import warnings
 from typing import Callable, Dict, Optional
@@ -20,6 +21,15 @@ import torch
 
 from . import solver as _solver
 from .geometry import SE3
+
+try:                                                                         # built by _cabi.build() / build_flatten()
+    from . import _vb_flatten
+except ImportError:                                                          # host logic only: the list-comprehension
+    _vb_flatten = None                                                       # flatten below is the same statement
+
+
+def _as_f64(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
 
 __all__ = ["bipartite_se3sync", "object_bipartite_se3sync", "large_bipartite_so3sync", "EdgeTable", "solve_table",
            "last_info", "EigenConvergenceWarning"]
@@ -45,9 +55,28 @@ class EdgeTable:
                 gc.enable()
 
     def _from_dict(self, src_edges, constraints, noise_model_r, noise_model_t, edge_filter):
-        # one pass of list comprehensions over the dictionary (insertion order, like the reference's
-        # loops); the callables see exactly the kept detections: edge_filter once per detection,
-        # the noise models once per KEPT detection (bipgo.py:204, :212, :423, :449)
+        # One pass over the dictionary in insertion order, like the reference's loops; the callables see exactly
+        # the kept detections: edge_filter once per detection, the noise models once per KEPT detection
+        # (bipgo.py:204, :212, :423, :449).  The walk itself runs in C (csrc/flatten.c: key coding, pose copies,
+        # weights) -- what remains per detection is the caller's own callables.
+        if _vb_flatten is None or os.environ.get("VICAN_B200_PY_FLATTEN", "0") == "1":
+            return self._from_dict_py(src_edges, constraints, noise_model_r, noise_model_t, edge_filter)
+        n = len(src_edges)
+        R = np.empty((n, 9), dtype=np.float64)
+        t = np.empty((n, 3), dtype=np.float64)
+        kr = np.empty(n, dtype=np.float64)
+        kt = np.empty(n, dtype=np.float64)
+        cam_code = np.empty(n, dtype=np.int32)
+        tm_code = np.empty(n, dtype=np.int32)
+        k, cam_keys, tm_keys, r_fmt, kr0 = _vb_flatten.flatten(src_edges, edge_filter, noise_model_r, noise_model_t,
+                                                               _as_f64, R, t, kr, kt, cam_code, tm_code)
+        if k == 0:
+            raise ValueError("no edge passes edge_filter")
+        self._assemble_coded(cam_keys, cam_code[:k], tm_keys, tm_code[:k], R[:k], t[:k], kr[:k], kt[:k], constraints,
+                             round_kr_f32=bool(r_fmt == "f" and not isinstance(kr0, np.floating)))
+
+    def _from_dict_py(self, src_edges, constraints, noise_model_r, noise_model_t, edge_filter):
+        # the same flatten as list comprehensions (kept as the statement the C walk is tested against)
         kept = [kv for kv in src_edges.items() if edge_filter(kv[1])]
         if not kept:
             raise ValueError("no edge passes edge_filter")
@@ -72,16 +101,36 @@ class EdgeTable:
         return self
 
     def _assemble(self, cams, tm_keys, Rs, ts, kr, kt, constraints):
-        self.root = str(min(list(constraints.keys())))                       # bipgo.py:411 (string min)
-        self.n_raw = n = len(cams)
+        n = len(cams)
         if n == 0:
             raise ValueError("no edge passes edge_filter")
+        if isinstance(Rs, list) and len({r.dtype for r in Rs}) > 1:
+            # the float32 rounding of `k_r * pose.R()` is mirrored per CALL, not per detection
+            raise ValueError("detections mix float32 and float64 pose arrays; convert them to one dtype")
+        R = np.array(Rs) if isinstance(Rs, list) else Rs                     # np.array: 2.5x faster than np.stack here
+        # detections are coded through dictionaries of the DISTINCT key components (first-seen order)
+        cam_keys = list(dict.fromkeys(cams))
+        tm_dist = list(dict.fromkeys(tm_keys))
+        cpos = {c: i for i, c in enumerate(cam_keys)}
+        tmpos = {s: i for i, s in enumerate(tm_dist)}
+        cam_code = np.fromiter(map(cpos.__getitem__, cams), dtype=np.int32, count=n)
+        tm_code = np.fromiter(map(tmpos.__getitem__, tm_keys), dtype=np.int32, count=n)
+        self._assemble_coded(cam_keys, cam_code, tm_dist, tm_code, R.astype(np.float64).reshape(-1, 9),
+                             (np.array(ts) if isinstance(ts, list) else ts).astype(np.float64).reshape(-1, 3),
+                             np.asarray(kr, dtype=np.float64), np.asarray(kt, dtype=np.float64), constraints,
+                             round_kr_f32=bool(R.dtype == np.float32 and not isinstance(kr[0], np.floating)))
+
+    def _assemble_coded(self, cam_keys, cam_code, tm_keys, tm_code, R, t, kr, kt, constraints, round_kr_f32):
+        """cam_keys / tm_keys: DISTINCT camera ids and "<timestamp>_<marker>" strings; cam_code / tm_code: one index
+        into them per kept detection; R [n,9], t [n,3], kr, kt float64."""
+        self.root = str(min(list(constraints.keys())))                       # bipgo.py:411 (string min)
+        self.n_raw = int(cam_code.shape[0])
         # "timestamp_marker" strings repeat once per observing camera: split each distinct one once
-        split = {}
-        for s in dict.fromkeys(tm_keys):
+        split = []
+        for s in tm_keys:
             parts = s.split("_")                                             # bipgo.py:206-207
             constraints[parts[1]]                                            # KeyError like bipgo.py:209
-            split[s] = (parts[0], parts[1])
+            split.append((parts[0], parts[1]))
         # Camera order = np.unique over 'c'+id strings (bipgo.py:225-229; the one-letter prefix does not
         # change the order): index 0 is the gauge camera.  Time nodes are labelled in the order of the
         # TRANSLATION unknowns, np.unique over t+'_0' (bipgo.py:420-430), which differs from the
@@ -89,32 +138,29 @@ class EdgeTable:
         # '10_0' but 't1' < 't10').  The rotation stage does not depend on how time nodes are
         # labelled; the replayed CSR product of the translation CG does (its row sums run over
         # ascending unknown index, csrc/cg.cuh), so node indices ascend with the unknown index.
-        # np.unique runs on the DISTINCT ids only; detections are coded through dictionaries.
-        self.cam_ids = np.unique(np.asarray(list(dict.fromkeys(cams))))
-        tids = np.unique(np.asarray([t + "_0" for t in dict.fromkeys(p[0] for p in split.values())]))
-        self.time_ids = np.asarray([t[:-2] for t in tids])
-        self.marker_ids = sorted({p[1] for p in split.values()} | {self.root})
+        # np.unique runs on the DISTINCT ids only.
+        self.cam_ids = np.unique(np.asarray(cam_keys))
+        tids = np.unique(np.asarray([t_ + "_0" for t_ in dict.fromkeys(p[0] for p in split)]))
+        self.time_ids = np.asarray([t_[:-2] for t_ in tids])
+        self.marker_ids = sorted({p[1] for p in split} | {self.root})
         cpos = {str(c): i for i, c in enumerate(self.cam_ids)}
-        tpos = {str(t): i for i, t in enumerate(self.time_ids)}
+        tpos = {str(t_): i for i, t_ in enumerate(self.time_ids)}
         mpos = {m: i for i, m in enumerate(self.marker_ids)}
-        tcode = {s: tpos[p[0]] for s, p in split.items()}
-        mcode = {s: mpos[p[1]] for s, p in split.items()}
-        self.cam_idx = np.fromiter(map(cpos.__getitem__, cams), dtype=np.int32, count=n)
-        self.time_idx = np.fromiter(map(tcode.__getitem__, tm_keys), dtype=np.int32, count=n)
-        self.marker_idx = np.fromiter(map(mcode.__getitem__, tm_keys), dtype=np.int32, count=n)
-        if isinstance(Rs, list) and len({r.dtype for r in Rs}) > 1:
-            # the float32 rounding of `k_r * pose.R()` is mirrored per CALL, not per detection
-            raise ValueError("detections mix float32 and float64 pose arrays; convert them to one dtype")
-        R = np.array(Rs) if isinstance(Rs, list) else Rs                     # np.array: 2.5x faster than np.stack here
+        cam_remap = np.fromiter((cpos[c] for c in cam_keys), dtype=np.int32, count=len(cam_keys))
+        t_remap = np.fromiter((tpos[p[0]] for p in split), dtype=np.int32, count=len(split))
+        m_remap = np.fromiter((mpos[p[1]] for p in split), dtype=np.int32, count=len(split))
+        self.cam_idx = cam_remap[cam_code]
+        self.time_idx = t_remap[tm_code]
+        self.marker_idx = m_remap[tm_code]
         # numpy evaluates `k_r * pose.R()` in float32 when the pose arrays are float32 (poses
         # that went through SE3.inv(), geometry.py:209-211) and k_r is a Python float.  Only that first
         # product is rounded here; the reference's float32 chain also rounds the two constraint products
         # when the constraints are float32 arrays (deviation <= 1e-7 rad, tests/golden f32 case).
-        self.round_kr_f32 = bool(R.dtype == np.float32 and not isinstance(kr[0], np.floating))
-        self.R = R.astype(np.float64).reshape(-1, 9)
-        self.t = (np.array(ts) if isinstance(ts, list) else ts).astype(np.float64).reshape(-1, 3)
-        self.k_r = np.asarray(kr, dtype=np.float64)
-        self.k_t = np.asarray(kt, dtype=np.float64)
+        self.round_kr_f32 = bool(round_kr_f32)
+        self.R = R
+        self.t = t
+        self.k_r = kr
+        self.k_t = kt
         # per-marker constants (<= a few dozen): same numpy expressions as the reference
         R0 = np.asarray(constraints[self.root].R())
         self.markerC = np.stack([np.asarray(constraints[m].R(), dtype=np.float64).T @ R0.astype(np.float64)
