@@ -313,7 +313,7 @@ def main():
         return run_reference(args)
 
     import torch
-    from vican_b200 import _cabi, dist as vdist, solver
+    from vican_b200 import _cabi, dist as vdist, hostmem, solver
     from vican_b200.synthetic_device import make_scaled_network
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
@@ -324,6 +324,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # N ranks upload their shards at once (e2e arm): keep every rank's pinned buffers on its GPU's NUMA node
+    placement = hostmem.bind_to_gpu_node(local) if world > 1 else None
     lib = _cabi.lib()
     comm = vdist.create_comm()
     import torch.distributed as tdist
@@ -520,6 +522,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "gpu_launches_source": "vb_launch_count(): the library's own tally of executed vb:: kernels (CUB excluded)",
             "roofline": roofline, "cpu_baseline": cb, "multi_gpu_check": mg_check, "configs": cfg_block,
+            "host_placement": placement,
         }
         emit(line)
     vdist.destroy_comm(comm)

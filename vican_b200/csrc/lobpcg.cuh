@@ -28,7 +28,8 @@ namespace cg = cooperative_groups;
 constexpr int LOB_THREADS = 256;
 constexpr int LOB_NRED = 112;      // >= 12*9 + 1
 // persistent small state (doubles)
-constexpr int SM_THETA = 0, SM_RESN = 3, SM_CONV = 6, SM_ANORM = 7, SM_ITERS = 8, SM_ACT = 9, SM_TIME = 18, SM_SIZE = 32;
+constexpr int SM_THETA = 0, SM_RESN = 3, SM_CONV = 6, SM_ANORM = 7, SM_ITERS = 8, SM_ACT = 9, SM_TIME = 18, SM_NCONV = 29, SM_SIZE = 32;
+// SM_NCONV = 1 - SM_CONV: skip flag of launches that are only valid once the step HAS converged (so3sync_run)
 // SM_TIME..+9: globaltimer stamps (ns) of block 0 at the stage boundaries of the last step (diagnostics)
 
 struct LobpcgParams {
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(LOB_THREADS, 1) lobpcg_step_kernel(LobpcgParam
             p.small[SM_THETA] = theta_s[0]; p.small[SM_THETA + 1] = theta_s[1]; p.small[SM_THETA + 2] = theta_s[2];
             p.small[SM_RESN] = r0; p.small[SM_RESN + 1] = r1; p.small[SM_RESN + 2] = r2;
             p.small[SM_CONV] = (double)conv_s;
+            p.small[SM_NCONV] = (double)(1 - conv_s);
             p.small[SM_ANORM] = anorm;
             p.small[SM_ITERS] = p.first ? 1.0 : p.small[SM_ITERS] + 1.0;
             for (int j = 0; j < 3; ++j) p.small[SM_ACT + 6 + j] = (double)actP_s[j];

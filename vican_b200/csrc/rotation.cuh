@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(NODE_THREADS) gauge_project_kernel(const doubl
 
 // Y_c <- Y_c R0^T for every camera block (R0: 9 doubles on the device).  Used when the eigen-iteration
 // accepts its start block unchanged: see the shortcut in so3sync_run.
-__global__ void __launch_bounds__(NODE_THREADS) rotate_right_transposed_kernel(double* __restrict__ Y, const double* __restrict__ R0, int64_t n_c) {
+__global__ void __launch_bounds__(NODE_THREADS) rotate_right_transposed_kernel(double* __restrict__ Y, const double* __restrict__ R0, int64_t n_c,
+                                                                               const double* __restrict__ skip_flag = nullptr) {
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;   // speculative launch (see so3sync_run)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_c) return;
     double m[9], r0[9], o[9];
@@ -148,7 +150,9 @@ __global__ void __launch_bounds__(1024) deflate_kernel(const double* __restrict_
 
 // bipgo.py:306-315
 __global__ void __launch_bounds__(NODE_THREADS) primal_update_kernel(const double* __restrict__ M, double* __restrict__ r_c, double* __restrict__ lamC,
-                                     double* __restrict__ lamCinv, int64_t n_c, double* __restrict__ r12 = nullptr) {
+                                     double* __restrict__ lamCinv, int64_t n_c, double* __restrict__ r12 = nullptr,
+                                     const double* __restrict__ skip_flag = nullptr) {
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;   // speculative launch (see so3sync_run)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_c) return;
     double m[9], rot[9], sp[9], si[9];
@@ -177,7 +181,8 @@ __device__ __forceinline__ void ld_row256_plain(const double* p, double& a, doub
     (void)pad;
 }
 __global__ void __launch_bounds__(NODE_THREADS) dual_update_kernel(const double* Yt12, double* __restrict__ r_t, double* __restrict__ lamT, double* Wt12,
-                                   int64_t n_t) {
+                                   int64_t n_t, const double* __restrict__ skip_flag = nullptr) {
+    if (skip_flag != nullptr && *skip_flag != 0.0) return;   // speculative launch (see so3sync_run); uniform over the grid
     __shared__ double sR[NODE_THREADS * 9], sL[NODE_THREADS * 9];
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x;
     const int64_t t = t0 + threadIdx.x;
@@ -364,6 +369,8 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
     lp.Wpad = w.Xpad;
     const int max_inner = opt->max_inner > 0 ? opt->max_inner : 200;
     static const bool lob_timing = getenv("VICAN_B200_LOBPCG_TIMING") != nullptr;   // diagnostics: stage times of every step
+    // VICAN_B200_SPEC=0: always speculate a second eigen-step, never the converged continuation (A/B switch)
+    static const bool spec_continue = !(getenv("VICAN_B200_SPEC") && atoi(getenv("VICAN_B200_SPEC")) == 0);
 
     double max_eval = 1.0;   // bipgo.py:280
     int last_inner[2] = {0, 0};   // steps of the last two outer iterations (inexact-inner verification)
@@ -410,7 +417,34 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         int inner = 1;            // steps whose work was (or will be) really executed
         int enqueued = 1;         // steps enqueued so far
         double hist[3] = {1e300, 1e300, 1e300};   // residuals of the last three steps (stagnation guard)
-        for (;;) {
+        // Once the outer iteration has settled, the eigen-iteration accepts its start block at the first step
+        // (3, 1, 1, ... steps per outer iteration).  After such an iteration the host no longer speculates a SECOND
+        // step but the converged CONTINUATION: the shortcut's primal multiply, the primal update, the raw time pass
+        // and the dual update are enqueued behind the first step with the step's not-converged flag as their skip
+        // flag, and only then is the step's status read.  The GPU runs straight through (no queue of no-op launches,
+        // no idle time while the host reacts); if the prediction fails the four launches returned at their first
+        // instruction and the regular loop below takes over.  No collective is ever speculated.
+        bool by_prediction = false;
+        if (spec_continue && opt->no_shortcut == 0 && outer >= 1 && last_inner[1] == 1 && !opt->eval_gap && !keep_Y) {
+            const double* nconv = w.small + SM_NCONV;
+            rotate_right_transposed_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, n_c, nconv);
+            primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, w.lamC, w.lamCinv, n_c, w.Xpad, nconv);
+            VB_KERNEL_CHECK();
+            VB_RC(time_pass(1, r_c, w.Wt, nconv, true));
+            if (n_t > 0) dual_update_kernel<<<node_grid(n_t), NODE_THREADS, 0, st>>>(w.Wt, r_t, w.lamT, w.Wt, n_t, nconv);
+            VB_KERNEL_CHECK();
+            VB_CHECK(cudaEventSynchronize(ps.ev[1 % STATUS_SLOTS]));
+            hs = ps.h + (1 % STATUS_SLOTS) * SM_SIZE;
+            if (hs[SM_CONV] != 0.0) {
+                by_prediction = true;
+                S->kernel_launches += 3;
+                S->shortcut_outer++;
+            } else {   // skipped on the device
+                S->time_passes--; S->kernel_launches--;
+                if (last_time_slot >= 0) prof_kind[last_time_slot] = -1;
+            }
+        }
+        while (!by_prediction) {
             bool speculated = false;
             if (enqueued < max_inner) {
                 VB_RC(time_pass(0, w.W, w.Wt, conv_flag, true));   // the step kernel wrote W into Xpad as well
@@ -504,7 +538,9 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
         // from: no gauge kernel, no time pass, no camera pass (2 instead of 4 edge passes per converged
         // outer iteration).  Y and the old r_c are still intact here (speculative passes leave Y alone).
         const bool shortcut = opt->no_shortcut == 0 && outer >= 1 && inner == 1 && hs[SM_CONV] != 0.0;
-        if (shortcut) {
+        if (by_prediction) {
+            // the continuation already ran behind the first step (see above)
+        } else if (shortcut) {
             if (keep_Y) VB_CHECK(cudaMemcpyAsync(w.Y, w.Ykeep, cbytes, cudaMemcpyDeviceToDevice, st));
             rotate_right_transposed_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, n_c);
             VB_KERNEL_CHECK();
@@ -515,12 +551,14 @@ inline int so3sync_run(const vb_graph* g, const vb_so3_options* opt, double* r_c
             VB_RC(time_pass(0, r_c, w.Wt, nullptr, true));
             VB_RC(cam_pass(w.Wt, w.Y));
         }
-        primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, w.lamC, w.lamCinv, n_c, w.Xpad);
-        VB_KERNEL_CHECK();
-        VB_RC(time_pass(1, r_c, w.Wt, nullptr, true));
-        if (n_t > 0) dual_update_kernel<<<node_grid(n_t), NODE_THREADS, 0, st>>>(w.Wt, r_t, w.lamT, w.Wt, n_t);
-        VB_KERNEL_CHECK();
-        S->kernel_launches += 3;
+        if (!by_prediction) {
+            primal_update_kernel<<<node_grid(n_c), NODE_THREADS, 0, st>>>(w.Y, r_c, w.lamC, w.lamCinv, n_c, w.Xpad);
+            VB_KERNEL_CHECK();
+            VB_RC(time_pass(1, r_c, w.Wt, nullptr, true));
+            if (n_t > 0) dual_update_kernel<<<node_grid(n_t), NODE_THREADS, 0, st>>>(w.Wt, r_t, w.lamT, w.Wt, n_t);
+            VB_KERNEL_CHECK();
+            S->kernel_launches += 3;
+        }
         VB_CHECK(cudaMemcpyAsync(w.X, r_c, cbytes, cudaMemcpyDeviceToDevice, st));
         S->outer_done = outer + 1;
     }
