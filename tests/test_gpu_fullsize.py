@@ -16,7 +16,8 @@ from oracle import vican_oracle as orc           # noqa: E402
 from vican_b200 import synthetic as syn          # noqa: E402
 from vican_b200.geometry import SE3              # noqa: E402
 
-from util import ROT_TOL_RAD, TRANS_REL_TOL, callables, compare, geodesic_rad, rel_translation_err  # noqa: E402
+from util import (ROT_TOL_RAD, TRANS_REL_TOL, callables, compare, geodesic_rad, load_full_golden,  # noqa: E402
+                  rel_translation_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -49,15 +50,29 @@ def _run_dict(cfg, scale, solver=None, maxiter=None):
     return out, ref, info_dev, info, (edges, constraints, p, g)
 
 
+def _vs_real_reference(out, golden, g, tr_tol, oracle_out=None, rot_tol=1e-9):
+    """The same result against the answer of the REAL reference on the same (regenerated, digest-checked) inputs
+    (tests/golden/make_golden_fullsize.py); with ``oracle_out`` the oracle is pinned to it as well."""
+    ref, _ = load_full_golden(golden, g)
+    rot, tr = compare(out, ref)
+    assert rot <= rot_tol and tr <= tr_tol, (golden, rot, tr)
+    if oracle_out is not None:
+        rot, tr = compare(oracle_out, ref)
+        assert rot <= rot_tol and tr <= tr_tol, ("oracle", golden, rot, tr)
+
+
 @pytest.mark.parametrize("solver", ["direct", "conjugate_gradient"])
 def test_cfg1_full_size(cuda, solver):
     """small_room shape: 20 cameras, 5 000 timesteps, 105 000 detections, maxiter 10."""
-    out, ref, info_dev, info, _ = _run_dict("cfg1", 1.0, solver)
+    out, ref, info_dev, info, ctx = _run_dict("cfg1", 1.0, solver)
     rot, tr = compare(out, ref)
     assert rot <= ROT_TOL_RAD and tr <= TRANS_REL_TOL, (rot, tr, info_dev)
     assert rot <= 1e-9 and tr <= 2e-7, (rot, tr)
     if solver == "direct":
         assert info_dev["trans_iters"] == info["itn"] and info_dev["trans_istop"] == info["istop"]
+    # (scipy's lsqr amplifies rounding-level differences of its inputs to ~1e-7: only the contract is asserted for it)
+    _vs_real_reference(out, "full_cfg1_direct" if solver == "direct" else "full_cfg1_cg", ctx[3],
+                       TRANS_REL_TOL if solver == "direct" else 2e-7)
 
 
 def test_cfg2_full_size_and_bitwise_reproducible(cuda):
@@ -75,24 +90,28 @@ def test_cfg2_full_size_and_bitwise_reproducible(cuda):
     assert info_dev["trans_iters"] == bipgo.last_info["trans_iters"]
     for k in out:
         assert np.array_equal(out[k].t(), out2[k].t()) and np.array_equal(out[k].R(), out2[k].R()), k
+    _vs_real_reference(out, "full_cfg2", g, 2e-7)
 
 
 def test_cfg3_full_size(cuda):
     """large_shop shape: 200 cameras, 10 000 timesteps, 24-marker cube, 2 M detections, cg, maxiter 10."""
-    out, ref, info_dev, info, _ = _run_dict("cfg3", 1.0)
+    out, ref, info_dev, info, ctx = _run_dict("cfg3", 1.0)
     rot, tr = compare(out, ref)
     assert rot <= ROT_TOL_RAD and tr <= TRANS_REL_TOL, (rot, tr, info_dev)
     assert rot <= 1e-9 and tr <= 2e-7, (rot, tr)
+    _vs_real_reference(out, "full_cfg3", ctx[3], 2e-7, oracle_out=ref)
 
 
 def test_cfg5_tenth_convergence_stress(cuda):
     """cfg5: large_shop shape + 20 % outliers removed by edge_filter, maxiter = 500, at 10 % of the time
     nodes (200 cameras, 1 000 timesteps, 200 000 detections): the oracle's 500 dense eigen-solves finish
     in about a minute.  Full API (rotations + cg translations)."""
-    out, ref, info_dev, info, _ = _run_dict("cfg5", 0.1)
+    out, ref, info_dev, info, ctx = _run_dict("cfg5", 0.1)
     rot, tr = compare(out, ref)
     assert rot <= ROT_TOL_RAD and tr <= TRANS_REL_TOL, (rot, tr, info_dev)
     assert rot <= 1e-8, rot
+    # ... and against the REAL reference's 500 iterations on the same inputs
+    _vs_real_reference(out, "tenth_cfg5", ctx[3], TRANS_REL_TOL, oracle_out=ref, rot_tol=1e-8)
 
 
 def test_cfg4_twentieth_scale_matches_oracle(cuda):
