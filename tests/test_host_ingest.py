@@ -321,3 +321,61 @@ def test_c_flatten_call_counts_and_order(monkeypatch):
     kept = [id(v) for v in edges.values() if ef0(v)]
     assert seen["f"] == [id(v) for v in edges.values()]                  # insertion order, once each
     assert seen["r"] == kept and seen["t"] == kept
+
+
+def test_object_rekey_in_c_equals_the_python_loop(monkeypatch):
+    """object_bipartite_se3sync's re-key + invert step (bipgo.py:526-531): pose stacking and the new dictionary are built
+    in C (csrc/flatten.c: poses, rekey); same dictionary as the Python loop -- same key order, same field OBJECTS,
+    float32 pose containers with the same numbers.  The device batch inversion is replaced by numpy here (CPU test)."""
+    import torch
+    from vican_b200 import bipgo, ops
+
+    def fake_invert(R, t, round_f32=False):
+        R = np.asarray(R, np.float64).reshape(-1, 3, 3)
+        t = np.asarray(t, np.float64).reshape(-1, 3)
+        Ri = np.ascontiguousarray(np.transpose(R, (0, 2, 1)))
+        ti = -(Ri @ t[:, :, None])[:, :, 0]
+        if round_f32:
+            Ri, ti = Ri.astype(np.float32).astype(np.float64), ti.astype(np.float32).astype(np.float64)
+        return torch.from_numpy(Ri), torch.from_numpy(ti)
+
+    monkeypatch.setattr(ops, "se3_invert_batch", fake_invert)
+    g = syn.make_object_calibration(seed=3, n_times=60, n_markers=10, min_visible=3, max_visible=10)
+    edges, _ = syn.to_edge_dict(g, SE3)
+    keys = list(edges.keys())
+    edges[keys[5]] = dict(edges[keys[5]], pose=SE3(R=edges[keys[5]]["pose"].R().astype(np.float32),
+                                                   t=edges[keys[5]]["pose"].t()))          # np.stack would upcast it
+    root = str(min(int(k[1].split("_")[1]) for k in edges))
+    monkeypatch.setenv("VICAN_B200_PY_FLATTEN", "0")
+    assert bipgo._vb_flatten is not None
+    a = bipgo._rekey_inverted(edges, root)
+    monkeypatch.setenv("VICAN_B200_PY_FLATTEN", "1")
+    b = bipgo._rekey_inverted(edges, root)
+    assert list(a.keys()) == list(b.keys()) and len(a) == len(edges)
+    for (ka, va), (kb, vb), v0 in zip(a.items(), b.items(), edges.values()):
+        assert ka == kb and isinstance(ka, tuple) and list(va.keys()) == list(vb.keys()) == ["pose", "corners", "reprojected_err", "im_filename"]
+        assert va["corners"] is v0["corners"] and va["im_filename"] is v0["im_filename"] and va["reprojected_err"] is v0["reprojected_err"]
+        for f in ("R", "t"):
+            x, y = getattr(va["pose"], f)(), getattr(vb["pose"], f)()
+            assert x.dtype == y.dtype == np.float32 and np.array_equal(x, y)
+        assert va["pose"]._pose.dtype == np.float32 and np.array_equal(va["pose"]._pose, vb["pose"]._pose)
+        assert np.array_equal((va["pose"] @ va["pose"].inv())._pose, (vb["pose"] @ vb["pose"].inv())._pose)
+    # the full flatten of both dictionaries agrees as well
+    nr, nt, ef = syn.default_callables()
+    cons = {root: SE3(pose=np.eye(4))}
+    _same(EdgeTable(a, cons, nr, nt, ef), EdgeTable(b, cons, nr, nt, ef))
+    # errors of the Python loop: a missing field, a key that is not "t_m"
+    monkeypatch.setenv("VICAN_B200_PY_FLATTEN", "0")
+    bad = dict(edges)
+    bad[keys[0]] = {k: v for k, v in edges[keys[0]].items() if k != "corners"}
+    with pytest.raises(KeyError):
+        bipgo._rekey_inverted(bad, root)
+    with pytest.raises(ValueError):
+        bipgo._rekey_inverted({(keys[0][0], "7"): edges[keys[0]]}, root)
+    # float32 poses take the container's own inv() (numpy float32 arithmetic), C re-key only
+    e32 = {k: dict(v, pose=SE3(R=v["pose"].R().astype(np.float32), t=v["pose"].t().astype(np.float32))) for k, v in edges.items()}
+    c = bipgo._rekey_inverted(e32, root)
+    monkeypatch.setenv("VICAN_B200_PY_FLATTEN", "1")
+    d = bipgo._rekey_inverted(e32, root)
+    assert list(c.keys()) == list(d.keys())
+    assert all(np.array_equal(x["pose"]._pose, y["pose"]._pose) for x, y in zip(c.values(), d.values()))

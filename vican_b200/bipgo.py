@@ -317,29 +317,50 @@ def object_bipartite_se3sync(src_edges: dict, noise_model_r: Callable, noise_mod
     # bipgo.py:526-531: re-key and invert every pose.  SE3.inv() stores its result in a float32
     # 4x4 (geometry.py:239-243); fp64 poses are inverted as one device batch with the same
     # rounding, float32 poses keep numpy's float32 arithmetic via the container itself.
-    keys = list(src_edges.keys())
-    vals = [src_edges[k] for k in keys]
-    R0 = np.asarray(vals[0]["pose"].R()) if vals else None
-    if vals and R0.dtype == np.float64:
-        from . import ops
-        Ri, ti = ops.se3_invert_batch(np.stack([v["pose"].R() for v in vals]),
-                                      np.stack([np.asarray(v["pose"].t(), dtype=np.float64) for v in vals]),
-                                      round_f32=True)
-        P4 = np.zeros((len(vals), 4, 4), dtype=np.float32)
-        P4[:, :3, :3] = Ri.cpu().numpy()
-        P4[:, :3, 3] = ti.cpu().numpy()
-        P4[:, 3, 3] = 1.0
-        inv_poses = [SE3(pose=P4[i]) for i in range(len(vals))]
-    else:
-        inv_poses = [v["pose"].inv() for v in vals]
-    edges = {}
-    for k, v, ip in zip(keys, vals, inv_poses):
-        t, marker_id = k[1].split("_")
-        edges[marker_id, t + "_" + root] = {"pose": ip,
-                                            "corners": v["corners"],
-                                            "reprojected_err": v["reprojected_err"],
-                                            "im_filename": v["im_filename"]}
+    gc_was_on = gc.isenabled()
+    gc.disable()                       # tens of thousands of new containers: keep the cyclic collector off the big dict
+    try:
+        edges = _rekey_inverted(src_edges, root)
+    finally:
+        if gc_was_on:
+            gc.enable()
     out = bipartite_se3sync(edges, constraints={root: SE3(pose=np.eye(4))}, noise_model_r=noise_model_r,
                             noise_model_t=noise_model_t, edge_filter=edge_filter, maxiter=maxiter,
                             lsqr_solver=lsqr_solver, dtype=dtype, mode=mode, strict=strict, verbose=verbose)
     return {k: v for k, v in out.items() if "_" not in k}                    # bipgo.py:543
+
+
+def _rekey_inverted(src_edges: dict, root: str) -> dict:
+    """bipgo.py:526-531: {(marker, "t_root"): {pose: inverted pose, corners, reprojected_err, im_filename}}."""
+    keys = list(src_edges.keys())
+    vals = list(src_edges.values())
+    use_c = _vb_flatten is not None and os.environ.get("VICAN_B200_PY_FLATTEN", "0") != "1"
+    R0 = np.asarray(vals[0]["pose"].R()) if vals else None
+    if vals and R0.dtype == np.float64:
+        from . import ops
+        if use_c:                                                            # pose arrays stacked in C (csrc/flatten.c)
+            Rs = np.empty((len(vals), 3, 3), dtype=np.float64)
+            ts = np.empty((len(vals), 3), dtype=np.float64)
+            _vb_flatten.poses(vals, _as_f64, Rs, ts)
+        else:
+            Rs = np.stack([v["pose"].R() for v in vals])
+            ts = np.stack([np.asarray(v["pose"].t(), dtype=np.float64) for v in vals])
+        Ri, ti = ops.se3_invert_batch(Rs, ts, round_f32=True)
+        P4 = np.zeros((len(vals), 4, 4), dtype=np.float32)
+        P4[:, :3, :3] = Ri.cpu().numpy()
+        P4[:, :3, 3] = ti.cpu().numpy()
+        P4[:, 3, 3] = 1.0
+        inv_poses = list(map(SE3._from_pose32, P4))
+    else:
+        inv_poses = [v["pose"].inv() for v in vals]
+    if use_c:
+        edges = _vb_flatten.rekey(keys, vals, inv_poses, root)
+    else:
+        edges = {}
+        for k, v, ip in zip(keys, vals, inv_poses):
+            t, marker_id = k[1].split("_")
+            edges[marker_id, t + "_" + root] = {"pose": ip,
+                                                "corners": v["corners"],
+                                                "reprojected_err": v["reprojected_err"],
+                                                "im_filename": v["im_filename"]}
+    return edges

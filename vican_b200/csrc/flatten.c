@@ -191,8 +191,95 @@ done:
     return result;
 }
 
+/* poses(vals, as_f64, R_out, t_out) -> r_format
+ * Copies value["pose"].R() / .t() of every detection of the LIST `vals` into float64 R_out[n][9], t_out[n][3] (what
+ * object_bipartite_se3sync needs to invert all poses as one device batch, bipgo.py:526-531), float32 arrays converted
+ * exactly (what np.stack's upcast does).  Returns the common struct format of the R arrays, '?' if they differ. */
+static PyObject *poses(PyObject *self, PyObject *args)
+{
+    PyObject *vals, *as_f64, *oR, *ot;
+    if (!PyArg_ParseTuple(args, "O!OOO", &PyList_Type, &vals, &as_f64, &oR, &ot)) return NULL;
+    const Py_ssize_t n = PyList_GET_SIZE(vals);
+    outbuf b[2];
+    memset(b, 0, sizeof(b));
+    PyObject *result = NULL;
+    char r_fmt = 0;
+    if (get_out(oR, &b[0], n * 72, "R_out") || get_out(ot, &b[1], n * 24, "t_out")) goto done;
+    double *R = (double *)b[0].v.buf, *t = (double *)b[1].v.buf;
+    for (Py_ssize_t k = 0; k < n; ++k) {
+        if (k >= PyList_GET_SIZE(vals)) { PyErr_SetString(PyExc_RuntimeError, "list changed size"); goto done; }
+        PyObject *pose = PyObject_GetItem(PyList_GET_ITEM(vals, k), s_pose);
+        if (!pose) goto done;
+        PyObject *Ro = PyObject_CallMethodNoArgs(pose, s_R);
+        PyObject *to = Ro ? PyObject_CallMethodNoArgs(pose, s_t) : NULL;
+        Py_DECREF(pose);
+        char fmt = '?';
+        int rc = (Ro && to) ? (copy_pose_part(Ro, as_f64, R + 9 * k, 3, 3, &fmt) || copy_pose_part(to, as_f64, t + 3 * k, 3, 1, NULL)) : -1;
+        Py_XDECREF(Ro); Py_XDECREF(to);
+        if (rc) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "bad pose arrays"); goto done; }
+        if (k == 0) r_fmt = fmt;
+        else if (fmt != r_fmt) r_fmt = '?';          /* mixed dtypes: values are converted like np.stack's upcast */
+    }
+    {
+        char fs[2] = { r_fmt ? r_fmt : 'd', 0 };
+        result = PyUnicode_FromString(fs);
+    }
+done:
+    for (int i = 0; i < 2; ++i) if (b[i].held) PyBuffer_Release(&b[i].v);
+    return result;
+}
+
+/* rekey(keys, vals, inv_poses, root) -> dict
+ * The re-keyed detection dictionary of object_bipartite_se3sync (bipgo.py:526-531): for key (c, "t_m") and value v,
+ *     out[(m, t + "_" + root)] = {"pose": inv_poses[i], "corners": v["corners"], "reprojected_err": v["reprojected_err"],
+ *                                 "im_filename": v["im_filename"]}
+ * in the order of the lists (a repeated new key keeps the later detection, like the reference's dict assignment).
+ * Missing fields raise KeyError, a second key component that is not "t_m" raises ValueError, as the Python loop does. */
+static PyObject *rekey(PyObject *self, PyObject *args)
+{
+    PyObject *keys, *vals, *inv, *root;
+    if (!PyArg_ParseTuple(args, "O!O!O!U", &PyList_Type, &keys, &PyList_Type, &vals, &PyList_Type, &inv, &root)) return NULL;
+    const Py_ssize_t n = PyList_GET_SIZE(keys);
+    if (PyList_GET_SIZE(vals) != n || PyList_GET_SIZE(inv) != n) {
+        PyErr_SetString(PyExc_ValueError, "keys, vals and inv_poses must have the same length");
+        return NULL;
+    }
+    PyObject *out = PyDict_New(), *sep = PyUnicode_FromString("_");
+    PyObject *s_corners = PyUnicode_InternFromString("corners"), *s_err = PyUnicode_InternFromString("reprojected_err");
+    PyObject *s_im = PyUnicode_InternFromString("im_filename");
+    PyObject *tail = sep ? PyUnicode_Concat(sep, root) : NULL;          /* "_" + root */
+    int ok = out && sep && s_corners && s_err && s_im && tail;
+    for (Py_ssize_t i = 0; ok && i < n; ++i) {
+        PyObject *k1 = PySequence_GetItem(PyList_GET_ITEM(keys, i), 1);
+        PyObject *parts = k1 ? PyUnicode_Split(k1, sep, -1) : NULL;
+        Py_XDECREF(k1);
+        if (!parts) { ok = 0; break; }
+        if (PyList_GET_SIZE(parts) != 2) {
+            PyErr_Format(PyExc_ValueError, "%s values to unpack (expected 2)", PyList_GET_SIZE(parts) < 2 ? "not enough" : "too many");
+            Py_DECREF(parts); ok = 0; break;
+        }
+        PyObject *tkey = PyUnicode_Concat(PyList_GET_ITEM(parts, 0), tail);
+        PyObject *nk = tkey ? PyTuple_Pack(2, PyList_GET_ITEM(parts, 1), tkey) : NULL;
+        Py_XDECREF(tkey); Py_DECREF(parts);
+        PyObject *v = PyList_GET_ITEM(vals, i);
+        PyObject *c = nk ? PyObject_GetItem(v, s_corners) : NULL;
+        PyObject *e = c ? PyObject_GetItem(v, s_err) : NULL;
+        PyObject *f = e ? PyObject_GetItem(v, s_im) : NULL;
+        PyObject *d = f ? PyDict_New() : NULL;
+        if (!d || PyDict_SetItem(d, s_pose, PyList_GET_ITEM(inv, i)) || PyDict_SetItem(d, s_corners, c) ||
+            PyDict_SetItem(d, s_err, e) || PyDict_SetItem(d, s_im, f) || PyDict_SetItem(out, nk, d))
+            ok = 0;
+        Py_XDECREF(nk); Py_XDECREF(c); Py_XDECREF(e); Py_XDECREF(f); Py_XDECREF(d);
+    }
+    Py_XDECREF(sep); Py_XDECREF(s_corners); Py_XDECREF(s_err); Py_XDECREF(s_im); Py_XDECREF(tail);
+    if (!ok) { Py_XDECREF(out); return NULL; }
+    return out;
+}
+
 static PyMethodDef methods[] = {
     {"flatten", flatten, METH_VARARGS, "one-pass flatten of a detection dictionary (see csrc/flatten.c)"},
+    {"poses", poses, METH_VARARGS, "stack pose.R() / pose.t() of a list of detections into float64 arrays"},
+    {"rekey", rekey, METH_VARARGS, "the re-keyed detection dictionary of object_bipartite_se3sync"},
     {NULL, NULL, 0, NULL}
 };
 

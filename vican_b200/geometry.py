@@ -42,6 +42,15 @@ class SE3:
             m[-1, -1] += 1.0
             self._pose = m
 
+    @classmethod
+    def _from_pose32(cls, m: np.ndarray) -> "SE3":
+        """``SE3(pose=m)`` for a float32 4x4 array the caller hands over (no copy: rows of a freshly built batch)."""
+        self = cls.__new__(cls)
+        self._pose = m
+        self._R = m[:3, :3]
+        self._t = m[:3, -1]
+        return self
+
     def __getstate__(self):
         return {"_pose": self._pose, "_R": self._R, "_t": self._t}
 
