@@ -379,3 +379,39 @@ def test_object_rekey_in_c_equals_the_python_loop(monkeypatch):
     d = bipgo._rekey_inverted(e32, root)
     assert list(c.keys()) == list(d.keys())
     assert all(np.array_equal(x["pose"]._pose, y["pose"]._pose) for x, y in zip(c.values(), d.values()))
+
+
+def test_object_host_path_end_to_end_against_the_oracle(monkeypatch):
+    """The host side of object_bipartite_se3sync (re-key + invert + hand-over to bipartite_se3sync + result filter,
+    bipgo.py:524-543) with the two device calls replaced -- batch inversion by numpy, the solve by the oracle's
+    bipartite_se3sync -- must reproduce the oracle's object_bipartite_se3sync on the original dictionary."""
+    import torch
+    from oracle import vican_oracle as orc
+    from vican_b200 import bipgo, ops
+    from util import compare
+
+    def fake_invert(R, t, round_f32=False):
+        R = np.asarray(R, np.float64).reshape(-1, 3, 3)
+        t = np.asarray(t, np.float64).reshape(-1, 3)
+        Ri = np.ascontiguousarray(np.transpose(R, (0, 2, 1)))
+        ti = -(Ri @ t[:, :, None])[:, :, 0]
+        if round_f32:
+            Ri, ti = Ri.astype(np.float32).astype(np.float64), ti.astype(np.float32).astype(np.float64)
+        return torch.from_numpy(Ri), torch.from_numpy(ti)
+
+    def oracle_solve(edges, constraints, noise_model_r, noise_model_t, edge_filter, maxiter, lsqr_solver, dtype=np.float32, **kw):
+        out = orc.bipartite_se3sync_oracle(edges, constraints, noise_model_r, noise_model_t, edge_filter, maxiter, lsqr_solver)
+        return {k: SE3(R=R.astype(dtype), t=t) for k, (R, t) in out.items()}
+
+    monkeypatch.setattr(ops, "se3_invert_batch", fake_invert)
+    monkeypatch.setattr(bipgo, "bipartite_se3sync", oracle_solve)
+    g = syn.make_object_calibration(seed=2, n_times=60, n_markers=10, min_visible=3, max_visible=10)
+    edges, _ = syn.to_edge_dict(g, SE3)
+    nr, nt, ef = syn.default_callables()
+    ref = orc.object_bipartite_se3sync_oracle(edges, nr, nt, ef, 3, "conjugate_gradient", se3_cls=SE3)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VICAN_B200_PY_FLATTEN", flag)
+        out = bipgo.object_bipartite_se3sync(edges, nr, nt, ef, maxiter=3, lsqr_solver="conjugate_gradient", dtype=np.float64)
+        assert sorted(out.keys()) == sorted(ref.keys()) and all("_" not in k for k in out)
+        rot, tr = compare(out, ref)
+        assert rot <= 1e-12 and tr <= 1e-10, (flag, rot, tr)
